@@ -1,0 +1,429 @@
+// givepose_b200 -- C-ABI entry points (include/givepose_b200.h): argument checks, kernel selection,
+// launches.  Host-side counterpart of the reference's network/ops_dcnv3/src/cuda/dcnv3_cuda.cu:21-174,
+// without the im2col_step chunk loop (the flat offset/mask addressing makes chunking a no-op) and without
+// the at::zeros memset of an output that is fully overwritten (dcnv3_cuda.cu:55-57).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "dcnv3_kernels.cuh"
+
+namespace gp {
+unsigned long long g_launches = 0;
+
+struct Tuning {
+    int tile_h = 8, tile_w = 8, gs = 1;
+    bool init = false;
+};
+static Tuning g_tune;
+
+static void init_tuning() {
+    if (g_tune.init) return;
+    g_tune.init = true;
+    if (const char *e = getenv("GP_TILE_H")) g_tune.tile_h = atoi(e);
+    if (const char *e = getenv("GP_TILE_W")) g_tune.tile_w = atoi(e);
+    if (const char *e = getenv("GP_GS")) g_tune.gs = atoi(e);
+}
+
+static int make_params(const gp_dcnv3_desc *d, KParams &p) {
+    if (!d) return GP_ERR_NULL;
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->G <= 0 || d->gc <= 0 || d->kh <= 0 || d->kw <= 0 || d->sh <= 0 ||
+        d->sw <= 0 || d->dh <= 0 || d->dw <= 0 || d->ph < 0 || d->pw < 0)
+        return GP_ERR_SHAPE;
+    if (d->remove_center != 0 && d->remove_center != 1) return GP_ERR_SHAPE;
+    if (d->remove_center && (d->kh % 2 == 0 || d->kw % 2 == 0 || d->kh != d->kw)) return GP_ERR_UNSUPPORTED;
+    if (d->Ho != gp_dcnv3_out_size(d->H, d->kh, d->sh, d->ph, d->dh) ||
+        d->Wo != gp_dcnv3_out_size(d->W, d->kw, d->sw, d->pw, d->dw) || d->Ho <= 0 || d->Wo <= 0)
+        return GP_ERR_SHAPE;
+    memset(&p, 0, sizeof(p));
+    p.N = d->N; p.H = d->H; p.W = d->W; p.G = d->G; p.gc = d->gc; p.C = d->G * d->gc;
+    p.kh = d->kh; p.kw = d->kw; p.sh = d->sh; p.sw = d->sw; p.ph = d->ph; p.pw = d->pw; p.dh = d->dh; p.dw = d->dw;
+    p.remove_center = d->remove_center;
+    p.P = d->kh * d->kw - d->remove_center;
+    p.Ho = d->Ho; p.Wo = d->Wo;
+    p.half_h = (d->dh * (d->kh - 1)) >> 1;
+    p.half_w = (d->dw * (d->kw - 1)) >> 1;
+    p.base_h = p.half_h - d->ph;
+    p.base_w = p.half_w - d->pw;
+    p.scale = d->offset_scale;
+    p.n_units = (long long)d->N * d->Ho * d->Wo * d->G;
+    if (p.P <= 0) return GP_ERR_SHAPE;
+    return GP_OK;
+}
+
+static size_t elem_size(int dtype) {
+    switch (dtype) {
+        case GP_F32: return 4;
+        case GP_BF16: case GP_F16: return 2;
+        case GP_F64: return 8;
+    }
+    return 0;
+}
+
+static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// can the tiled/vectorised kernels take this call?  fills the tiling fields of p.
+static bool plan_tiled(KParams &p, int dtype, int *L_out) {
+    if (dtype == GP_F64) return false;
+    const int vec = dtype == GP_F32 ? 4 : 8;
+    if (p.gc % vec) return false;
+    const int L = p.gc / vec;
+    if (L > 32 || (L & (L - 1))) return false;
+    if ((long long)p.H * p.W * p.C >= (1ll << 31)) return false;
+    init_tuning();
+    int th = g_tune.tile_h, tw = g_tune.tile_w, gs = g_tune.gs;
+    if (th < 1) th = 1;
+    if (tw < 1) tw = 1;
+    if (gs < 1) gs = 1;
+    while (gs > 1 && p.G % gs) --gs;
+    // keep staging under 48 KB of shared memory
+    while ((long long)th * tw * gs * p.P * 3 * 4 > 48 * 1024) {
+        if (gs > 1) { gs = 1; continue; }
+        if (th >= tw && th > 1) th = (th + 1) / 2; else if (tw > 1) tw = (tw + 1) / 2; else return false;
+    }
+    p.tile_h = th; p.tile_w = tw; p.gs = gs; p.gchunks = p.G / gs;
+    p.tiles_y = (p.Ho + th - 1) / th;
+    p.tiles_x = (p.Wo + tw - 1) / tw;
+    const long long ctas = (long long)p.N * p.tiles_y * p.tiles_x * p.gchunks;
+    if (ctas >= (1ll << 31)) return false;
+    *L_out = L;
+    return true;
+}
+
+static size_t tile_smem(const KParams &p) { return (size_t)p.tile_h * p.tile_w * p.gs * p.P * 3 * sizeof(float); }
+static unsigned tile_grid(const KParams &p) { return (unsigned)((long long)p.N * p.tiles_y * p.tiles_x * p.gchunks); }
+
+template <typename T, int VEC, bool SOFTMAX>
+static void launch_fwd_tile(const void *in, const void *off, const void *msk, void *out, const KParams &p, int L,
+                            cudaStream_t st) {
+    const bool k3 = p.kh == 3 && p.kw == 3 && !p.remove_center;
+    const size_t sm = tile_smem(p);
+    const unsigned grid = tile_grid(p);
+#define GP_FWD(LL, K3)                                                                                         \
+    dcnv3_fwd_tile<T, VEC, LL, K3, SOFTMAX><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off,     \
+                                                                            (const T *)msk, (T *)out, p)
+#define GP_FWD_L(LL) do { if (k3) GP_FWD(LL, true); else GP_FWD(LL, false); } while (0)
+    switch (L) {
+        case 1: GP_FWD_L(1); break;
+        case 2: GP_FWD_L(2); break;
+        case 4: GP_FWD_L(4); break;
+        case 8: GP_FWD_L(8); break;
+        case 16: GP_FWD_L(16); break;
+        case 32: GP_FWD_L(32); break;
+    }
+#undef GP_FWD_L
+#undef GP_FWD
+    count_launch();
+}
+
+template <typename T, int VEC>
+static void launch_bwd_tile(const void *in, const void *off, const void *msk, const void *gout, float *gin, void *goff,
+                            void *gmsk, const KParams &p, int L, cudaStream_t st) {
+    const bool k3 = p.kh == 3 && p.kw == 3 && !p.remove_center;
+    const size_t sm = tile_smem(p);
+    const unsigned grid = tile_grid(p);
+#define GP_BWD(LL, K3)                                                                                          \
+    dcnv3_bwd_tile<T, VEC, LL, K3><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, \
+                                                                   (const T *)gout, gin, (T *)goff, (T *)gmsk, p)
+#define GP_BWD_L(LL) do { if (k3) GP_BWD(LL, true); else GP_BWD(LL, false); } while (0)
+    switch (L) {
+        case 1: GP_BWD_L(1); break;
+        case 2: GP_BWD_L(2); break;
+        case 4: GP_BWD_L(4); break;
+        case 8: GP_BWD_L(8); break;
+        case 16: GP_BWD_L(16); break;
+        case 32: GP_BWD_L(32); break;
+    }
+#undef GP_BWD_L
+#undef GP_BWD
+    count_launch();
+}
+
+template <typename T, bool SOFTMAX>
+static void launch_fwd_generic(const void *in, const void *off, const void *msk, void *out, const KParams &p,
+                               cudaStream_t st) {
+    const long long total = p.n_units * p.gc;
+    const long long blocks = (total + 255) / 256;
+    const unsigned grid = (unsigned)(blocks > (1ll << 20) ? (1ll << 20) : blocks);
+    dcnv3_fwd_generic<T, SOFTMAX><<<grid, 256, 0, st>>>((const T *)in, (const T *)off, (const T *)msk, (T *)out, p);
+    count_launch();
+}
+
+template <typename T>
+static void launch_bwd_generic(const void *in, const void *off, const void *msk, const void *gout, void *gin_acc,
+                               void *goff, void *gmsk, const KParams &p, cudaStream_t st) {
+    const unsigned grid = (unsigned)(p.n_units > (1ll << 20) ? (1ll << 20) : p.n_units);
+    dcnv3_bwd_generic<T><<<grid, 64, 0, st>>>((const T *)in, (const T *)off, (const T *)msk, (const T *)gout,
+                                              (typename AccOf<T>::type *)gin_acc, (T *)goff, (T *)gmsk, p);
+    count_launch();
+}
+
+template <bool SOFTMAX>
+static int forward_impl(const void *in, const void *off, const void *msk, void *out, const gp_dcnv3_desc *d, int dtype,
+                        void *stream) {
+    if (!in || !off || !msk || !out) return GP_ERR_NULL;
+    if (!elem_size(dtype)) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(d, p)) return e;
+    if (!aligned16(in) || !aligned16(off) || !aligned16(msk) || !aligned16(out)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int L = 0;
+    if (plan_tiled(p, dtype, &L)) {
+        if (dtype == GP_F32) launch_fwd_tile<float, 4, SOFTMAX>(in, off, msk, out, p, L, st);
+        else if (dtype == GP_BF16) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
+        else launch_fwd_tile<__half, 8, SOFTMAX>(in, off, msk, out, p, L, st);
+    } else {
+        switch (dtype) {
+            case GP_F32: launch_fwd_generic<float, SOFTMAX>(in, off, msk, out, p, st); break;
+            case GP_BF16: launch_fwd_generic<__nv_bfloat16, SOFTMAX>(in, off, msk, out, p, st); break;
+            case GP_F16: launch_fwd_generic<__half, SOFTMAX>(in, off, msk, out, p, st); break;
+            case GP_F64: launch_fwd_generic<double, SOFTMAX>(in, off, msk, out, p, st); break;
+        }
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace gp
+
+using namespace gp;
+
+extern "C" {
+
+int gp_abi_version(void) { return GP_ABI_VERSION; }
+
+const char *gp_error_string(int code) {
+    switch (code) {
+        case GP_OK: return "ok";
+        case GP_ERR_NULL: return "givepose_b200: required pointer is NULL";
+        case GP_ERR_SHAPE: return "givepose_b200: inconsistent geometry (C != group*group_channels, bad dims or Ho/Wo)";
+        case GP_ERR_DTYPE: return "givepose_b200: unknown dtype";
+        case GP_ERR_ALIGN: return "givepose_b200: pointers must be 16-byte aligned";
+        case GP_ERR_WORKSPACE: return "givepose_b200: workspace too small";
+        case GP_ERR_UNSUPPORTED: return "givepose_b200: remove_center is only compatible with square odd kernel size";
+    }
+    if (code > 0) return cudaGetErrorString((cudaError_t)code);
+    return "givepose_b200: unknown error";
+}
+
+int gp_dcnv3_out_size(int size, int k, int stride, int pad, int dil) {
+    return (size + 2 * pad - (dil * (k - 1) + 1)) / stride + 1;
+}
+
+uint64_t gp_launch_count(void) { return g_launches; }
+void gp_launch_count_reset(void) { g_launches = 0; }
+
+int gp_set_tuning(int tile_h, int tile_w, int gs) {
+    init_tuning();
+    if (tile_h > 0) g_tune.tile_h = tile_h;
+    if (tile_w > 0) g_tune.tile_w = tile_w;
+    if (gs > 0) g_tune.gs = gs;
+    return GP_OK;
+}
+
+int gp_dcnv3_forward(const void *input, const void *offset, const void *mask, void *out, const gp_dcnv3_desc *desc,
+                     int dtype, void *stream) {
+    return forward_impl<false>(input, offset, mask, out, desc, dtype, stream);
+}
+
+int gp_dcnv3_forward_softmax(const void *input, const void *offset, const void *mask_logits, void *out,
+                             const gp_dcnv3_desc *desc, int dtype, void *stream) {
+    return forward_impl<true>(input, offset, mask_logits, out, desc, dtype, stream);
+}
+
+size_t gp_dcnv3_backward_workspace(const gp_dcnv3_desc *desc, int dtype) {
+    if (!desc || (dtype != GP_BF16 && dtype != GP_F16)) return 0;
+    return (size_t)desc->N * desc->H * desc->W * desc->G * desc->gc * sizeof(float);
+}
+
+int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, const void *grad_out, void *grad_input,
+                      void *grad_offset, void *grad_mask, size_t grad_offset_elems, size_t grad_mask_elems,
+                      void *workspace, size_t workspace_bytes, const gp_dcnv3_desc *desc, int dtype, void *stream) {
+    if (!input || !offset || !mask || !grad_out || !grad_input || !grad_offset || !grad_mask) return GP_ERR_NULL;
+    const size_t es = elem_size(dtype);
+    if (!es) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(desc, p)) return e;
+    if (!aligned16(input) || !aligned16(offset) || !aligned16(mask) || !aligned16(grad_out) || !aligned16(grad_input) ||
+        !aligned16(grad_offset) || !aligned16(grad_mask) || !aligned16(workspace))
+        return GP_ERR_ALIGN;
+    const size_t n_in = (size_t)p.N * p.H * p.W * p.C;
+    const size_t n_off = (size_t)p.n_units * p.P * 2, n_msk = (size_t)p.n_units * p.P;
+    if (grad_offset_elems < n_off || grad_mask_elems < n_msk) return GP_ERR_SHAPE;
+    const bool half16 = dtype == GP_BF16 || dtype == GP_F16;
+    if (half16 && (!workspace || workspace_bytes < n_in * sizeof(float))) return GP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+
+    // zero the accumulation target and the rows of grad_offset/grad_mask beyond the flat prefix
+    // (the reference zero-fills all three full tensors, dcnv3_cuda.cu:131-133; the prefix is fully overwritten here)
+    void *acc = half16 ? workspace : grad_input;
+    cudaError_t ce = cudaMemsetAsync(acc, 0, n_in * (half16 ? sizeof(float) : es), st);
+    if (ce != cudaSuccess) return (int)ce;
+    if (grad_offset_elems > n_off) {
+        ce = cudaMemsetAsync((char *)grad_offset + n_off * es, 0, (grad_offset_elems - n_off) * es, st);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    if (grad_mask_elems > n_msk) {
+        ce = cudaMemsetAsync((char *)grad_mask + n_msk * es, 0, (grad_mask_elems - n_msk) * es, st);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+
+    int L = 0;
+    if (plan_tiled(p, dtype, &L)) {
+        if (dtype == GP_F32) launch_bwd_tile<float, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else launch_bwd_tile<__half, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+    } else {
+        switch (dtype) {
+            case GP_F32: launch_bwd_generic<float>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
+            case GP_BF16: launch_bwd_generic<__nv_bfloat16>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
+            case GP_F16: launch_bwd_generic<__half>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
+            case GP_F64: launch_bwd_generic<double>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
+        }
+    }
+    ce = cudaGetLastError();
+    if (ce != cudaSuccess) return (int)ce;
+    if (half16) {
+        const long long n = (long long)n_in;
+        const unsigned grid = (unsigned)((n / 8 + 256) / 256);
+        if (dtype == GP_BF16) cast_from_f32<__nv_bfloat16><<<grid, 256, 0, st>>>((const float *)acc, (__nv_bfloat16 *)grad_input, n);
+        else cast_from_f32<__half><<<grid, 256, 0, st>>>((const float *)acc, (__half *)grad_input, n);
+        count_launch();
+        ce = cudaGetLastError();
+    }
+    return (int)ce;
+}
+
+int gp_dcnv3_sample_index(const void *offset, int32_t *hw_low, uint8_t *flags, const gp_dcnv3_desc *desc, int dtype,
+                          void *stream) {
+    if (!offset || !hw_low || !flags) return GP_ERR_NULL;
+    if (!elem_size(dtype)) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(desc, p)) return e;
+    cudaStream_t st = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((p.n_units + 255) / 256);
+    switch (dtype) {
+        case GP_F32: dcnv3_index_kernel<float><<<grid, 256, 0, st>>>((const float *)offset, hw_low, flags, p); break;
+        case GP_BF16: dcnv3_index_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)offset, hw_low, flags, p); break;
+        case GP_F16: dcnv3_index_kernel<__half><<<grid, 256, 0, st>>>((const __half *)offset, hw_low, flags, p); break;
+        case GP_F64: dcnv3_index_kernel<double><<<grid, 256, 0, st>>>((const double *)offset, hw_low, flags, p); break;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// ---- host-buffer entry points ---------------------------------------------------------------------------
+
+namespace {
+struct HostCache {
+    void *buf[8] = {nullptr};
+    size_t cap[8] = {0};
+    cudaStream_t stream = nullptr;
+    int device = -1;
+} g_hc;
+
+cudaError_t hc_get(int slot, size_t bytes, void **out) {
+    if (g_hc.cap[slot] < bytes) {
+        if (g_hc.buf[slot]) cudaFree(g_hc.buf[slot]);
+        g_hc.buf[slot] = nullptr;
+        g_hc.cap[slot] = 0;
+        cudaError_t e = cudaMalloc(&g_hc.buf[slot], bytes);
+        if (e != cudaSuccess) return e;
+        g_hc.cap[slot] = bytes;
+    }
+    *out = g_hc.buf[slot];
+    return cudaSuccess;
+}
+
+cudaError_t hc_begin(int device) {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return e;
+    if (g_hc.device != device) {
+        gp_host_cache_release();
+        g_hc.device = device;
+    }
+    if (!g_hc.stream) e = cudaStreamCreateWithFlags(&g_hc.stream, cudaStreamNonBlocking);
+    return e;
+}
+}  // namespace
+
+#define GP_CUDA(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return (int)e_; } while (0)
+
+int gp_host_cache_release(void) {
+    for (int i = 0; i < 8; ++i) {
+        if (g_hc.buf[i]) cudaFree(g_hc.buf[i]);
+        g_hc.buf[i] = nullptr;
+        g_hc.cap[i] = 0;
+    }
+    if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
+    g_hc.stream = nullptr;
+    g_hc.device = -1;
+    return GP_OK;
+}
+
+int gp_dcnv3_forward_host(const void *h_input, const void *h_offset, const void *h_mask, void *h_out,
+                          size_t offset_elems, size_t mask_elems, const gp_dcnv3_desc *desc, int dtype, int device) {
+    if (!h_input || !h_offset || !h_mask || !h_out) return GP_ERR_NULL;
+    const size_t es = elem_size(dtype);
+    if (!es) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(desc, p)) return e;
+    const size_t n_in = (size_t)p.N * p.H * p.W * p.C, n_out = (size_t)p.N * p.Ho * p.Wo * p.C;
+    const size_t n_off = (size_t)p.n_units * p.P * 2, n_msk = (size_t)p.n_units * p.P;
+    if (offset_elems < n_off || mask_elems < n_msk) return GP_ERR_SHAPE;
+    GP_CUDA(hc_begin(device));
+    void *d_in, *d_off, *d_msk, *d_out;
+    GP_CUDA(hc_get(0, n_in * es, &d_in));
+    GP_CUDA(hc_get(1, n_off * es, &d_off));   // only the flat prefix is ever read
+    GP_CUDA(hc_get(2, n_msk * es, &d_msk));
+    GP_CUDA(hc_get(3, n_out * es, &d_out));
+    cudaStream_t st = g_hc.stream;
+    GP_CUDA(cudaMemcpyAsync(d_in, h_input, n_in * es, cudaMemcpyHostToDevice, st));
+    GP_CUDA(cudaMemcpyAsync(d_off, h_offset, n_off * es, cudaMemcpyHostToDevice, st));
+    GP_CUDA(cudaMemcpyAsync(d_msk, h_mask, n_msk * es, cudaMemcpyHostToDevice, st));
+    if (int e = gp_dcnv3_forward(d_in, d_off, d_msk, d_out, desc, dtype, st)) return e;
+    GP_CUDA(cudaMemcpyAsync(h_out, d_out, n_out * es, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void *h_mask, const void *h_grad_out,
+                           void *h_grad_input, void *h_grad_offset, void *h_grad_mask, size_t offset_elems,
+                           size_t mask_elems, const gp_dcnv3_desc *desc, int dtype, int device) {
+    if (!h_input || !h_offset || !h_mask || !h_grad_out || !h_grad_input || !h_grad_offset || !h_grad_mask)
+        return GP_ERR_NULL;
+    const size_t es = elem_size(dtype);
+    if (!es) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(desc, p)) return e;
+    const size_t n_in = (size_t)p.N * p.H * p.W * p.C, n_out = (size_t)p.N * p.Ho * p.Wo * p.C;
+    const size_t n_off = (size_t)p.n_units * p.P * 2, n_msk = (size_t)p.n_units * p.P;
+    if (offset_elems < n_off || mask_elems < n_msk) return GP_ERR_SHAPE;
+    GP_CUDA(hc_begin(device));
+    void *d_in, *d_off, *d_msk, *d_go, *d_gi, *d_goff, *d_gmsk, *d_ws = nullptr;
+    GP_CUDA(hc_get(0, n_in * es, &d_in));
+    GP_CUDA(hc_get(1, n_off * es, &d_off));
+    GP_CUDA(hc_get(2, n_msk * es, &d_msk));
+    GP_CUDA(hc_get(3, n_out * es, &d_go));
+    GP_CUDA(hc_get(4, n_in * es, &d_gi));
+    GP_CUDA(hc_get(5, n_off * es, &d_goff));
+    GP_CUDA(hc_get(6, n_msk * es, &d_gmsk));
+    const size_t ws = gp_dcnv3_backward_workspace(desc, dtype);
+    if (ws) GP_CUDA(hc_get(7, ws, &d_ws));
+    cudaStream_t st = g_hc.stream;
+    GP_CUDA(cudaMemcpyAsync(d_in, h_input, n_in * es, cudaMemcpyHostToDevice, st));
+    GP_CUDA(cudaMemcpyAsync(d_off, h_offset, n_off * es, cudaMemcpyHostToDevice, st));
+    GP_CUDA(cudaMemcpyAsync(d_msk, h_mask, n_msk * es, cudaMemcpyHostToDevice, st));
+    GP_CUDA(cudaMemcpyAsync(d_go, h_grad_out, n_out * es, cudaMemcpyHostToDevice, st));
+    if (int e = gp_dcnv3_backward(d_in, d_off, d_msk, d_go, d_gi, d_goff, d_gmsk, n_off, n_msk, d_ws, ws, desc, dtype, st))
+        return e;
+    GP_CUDA(cudaMemcpyAsync(h_grad_input, d_gi, n_in * es, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(cudaMemcpyAsync(h_grad_offset, d_goff, n_off * es, cudaMemcpyDeviceToHost, st));
+    GP_CUDA(cudaMemcpyAsync(h_grad_mask, d_gmsk, n_msk * es, cudaMemcpyDeviceToHost, st));
+    // rows beyond the flat prefix are zero by contract (dcnv3_cuda.cu:131-133): host-side fill, nothing to transfer
+    if (offset_elems > n_off) memset((char *)h_grad_offset + n_off * es, 0, (offset_elems - n_off) * es);
+    if (mask_elems > n_msk) memset((char *)h_grad_mask + n_msk * es, 0, (mask_elems - n_msk) * es);
+    GP_CUDA(cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+}  // extern "C"
