@@ -13,6 +13,7 @@ unsigned long long g_launches = 0;
 
 struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 1;
+    int debug = 0;
     bool init = false;
 };
 static Tuning g_tune;
@@ -23,6 +24,7 @@ static void init_tuning() {
     if (const char *e = getenv("GP_TILE_H")) g_tune.tile_h = atoi(e);
     if (const char *e = getenv("GP_TILE_W")) g_tune.tile_w = atoi(e);
     if (const char *e = getenv("GP_GS")) g_tune.gs = atoi(e);
+    if (const char *e = getenv("GP_DEBUG")) g_tune.debug = atoi(e);   // profiling only: results are WRONG when set
 }
 
 static int make_params(const gp_dcnv3_desc *d, KParams &p) {
@@ -82,6 +84,7 @@ static bool plan_tiled(KParams &p, int dtype, int *L_out) {
         if (th >= tw && th > 1) th = (th + 1) / 2; else if (tw > 1) tw = (tw + 1) / 2; else return false;
     }
     p.tile_h = th; p.tile_w = tw; p.gs = gs; p.gchunks = p.G / gs;
+    p.debug = g_tune.debug;
     p.tiles_y = (p.Ho + th - 1) / th;
     p.tiles_x = (p.Wo + tw - 1) / tw;
     const long long ctas = (long long)p.N * p.tiles_y * p.tiles_x * p.gchunks;

@@ -302,6 +302,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                     s_w += gw * tg[c];        // cuh:145 (offset_scale applied after the channel sum)
                     s_h += gh * tg[c];        // cuh:146
                 }
+                if (!(p.debug & 1))
 #pragma unroll
                 for (int c4 = 0; c4 < VEC; c4 += 4) {   // cuh:116-140: one 16-byte reduction per corner
                     if (pt.flags & F_C1) red_add_v4(gin_g + base + c4, w1 * tg[c4], w1 * tg[c4 + 1], w1 * tg[c4 + 2], w1 * tg[c4 + 3]);
@@ -311,6 +312,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 }
             }
             // sum over the gc channels of the group = butterfly over the L lanes of this unit
+            if (!(p.debug & 2))
 #pragma unroll
             for (int o2 = L / 2; o2 > 0; o2 >>= 1) {
                 s_m += __shfl_xor_sync(0xffffffffu, s_m, o2);

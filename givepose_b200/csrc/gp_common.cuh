@@ -30,6 +30,7 @@ struct KParams {
     // tiling of the output plane used by the tiled kernels
     int tile_h, tile_w, tiles_y, tiles_x, gs /*groups per CTA*/, gchunks /*G/gs*/;
     long long n_units;       // N*Ho*Wo*G
+    int debug;               // profiling only (GP_DEBUG env): bit0 skip grad_input reductions, bit1 skip lane reductions
 };
 
 template <typename T> struct AccOf { using type = float; };
