@@ -39,7 +39,7 @@ EXPORTS = {
     "gp_dcnv3_forward_host": (_I, [_VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
     "gp_dcnv3_backward_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
     "gp_host_cache_release": (_I, []),
-    "gp_set_tuning": (_I, [_I, _I, _I]),
+    "gp_set_tuning": (_I, [_I, _I, _I, _I]),
     "gp_launch_count": (ctypes.c_uint64, []),
     "gp_launch_count_reset": (None, []),
 }

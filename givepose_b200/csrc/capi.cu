@@ -13,7 +13,7 @@ unsigned long long g_launches = 0;
 
 struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 1;
-    int debug = 0;
+    int vec16 = 8;   // channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
     bool init = false;
 };
 static Tuning g_tune;
@@ -24,7 +24,7 @@ static void init_tuning() {
     if (const char *e = getenv("GP_TILE_H")) g_tune.tile_h = atoi(e);
     if (const char *e = getenv("GP_TILE_W")) g_tune.tile_w = atoi(e);
     if (const char *e = getenv("GP_GS")) g_tune.gs = atoi(e);
-    if (const char *e = getenv("GP_DEBUG")) g_tune.debug = atoi(e);   // profiling only: results are WRONG when set
+    if (const char *e = getenv("GP_VEC16")) g_tune.vec16 = atoi(e) == 4 ? 4 : 8;
 }
 
 static int make_params(const gp_dcnv3_desc *d, KParams &p) {
@@ -65,42 +65,45 @@ static size_t elem_size(int dtype) {
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // can the tiled/vectorised kernels take this call?  fills the tiling fields of p.
-static bool plan_tiled(KParams &p, int dtype, int *L_out) {
+static bool plan_tiled(KParams &p, int dtype, int *L_out, int *vec_out) {
     if (dtype == GP_F64) return false;
-    const int vec = dtype == GP_F32 ? 4 : 8;
+    init_tuning();
+    int vec = dtype == GP_F32 ? 4 : g_tune.vec16;
+    if (vec == 8 && (p.gc % 8 || p.gc / 8 > 32) && p.gc % 4 == 0) vec = 4;
     if (p.gc % vec) return false;
     const int L = p.gc / vec;
     if (L > 32 || (L & (L - 1))) return false;
-    if ((long long)p.H * p.W * p.C >= (1ll << 31)) return false;
-    init_tuning();
+    if ((long long)p.H * p.W * p.C * 4 >= (1ll << 31)) return false;   // 32-bit byte offsets inside one image
     int th = g_tune.tile_h, tw = g_tune.tile_w, gs = g_tune.gs;
     if (th < 1) th = 1;
     if (tw < 1) tw = 1;
     if (gs < 1) gs = 1;
     while (gs > 1 && p.G % gs) --gs;
-    // keep staging under 48 KB of shared memory
-    while ((long long)th * tw * gs * p.P * 3 * 4 > 48 * 1024) {
+    // keep the sampling records under 48 KB of shared memory
+    while ((long long)th * tw * gs * (p.P * 24 + 8) > 48 * 1024) {
         if (gs > 1) { gs = 1; continue; }
         if (th >= tw && th > 1) th = (th + 1) / 2; else if (tw > 1) tw = (tw + 1) / 2; else return false;
     }
     p.tile_h = th; p.tile_w = tw; p.gs = gs; p.gchunks = p.G / gs;
-    p.debug = g_tune.debug;
     p.tiles_y = (p.Ho + th - 1) / th;
     p.tiles_x = (p.Wo + tw - 1) / tw;
     const long long ctas = (long long)p.N * p.tiles_y * p.tiles_x * p.gchunks;
     if (ctas >= (1ll << 31)) return false;
     *L_out = L;
+    *vec_out = vec;
     return true;
 }
 
-static size_t tile_smem(const KParams &p) { return (size_t)p.tile_h * p.tile_w * p.gs * p.P * 3 * sizeof(float); }
+static size_t tile_smem(const KParams &p, bool softmax) {
+    return (size_t)p.tile_h * p.tile_w * p.gs * (p.P * 24 + (softmax ? 8 : 0));
+}
 static unsigned tile_grid(const KParams &p) { return (unsigned)((long long)p.N * p.tiles_y * p.tiles_x * p.gchunks); }
 
 template <typename T, int VEC, bool SOFTMAX>
 static void launch_fwd_tile(const void *in, const void *off, const void *msk, void *out, const KParams &p, int L,
                             cudaStream_t st) {
-    const bool k3 = p.kh == 3 && p.kw == 3 && !p.remove_center;
-    const size_t sm = tile_smem(p);
+    const bool k3 = p.P == 9;
+    const size_t sm = tile_smem(p, SOFTMAX);
     const unsigned grid = tile_grid(p);
 #define GP_FWD(LL, K3)                                                                                         \
     dcnv3_fwd_tile<T, VEC, LL, K3, SOFTMAX><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off,     \
@@ -122,8 +125,8 @@ static void launch_fwd_tile(const void *in, const void *off, const void *msk, vo
 template <typename T, int VEC>
 static void launch_bwd_tile(const void *in, const void *off, const void *msk, const void *gout, float *gin, void *goff,
                             void *gmsk, const KParams &p, int L, cudaStream_t st) {
-    const bool k3 = p.kh == 3 && p.kw == 3 && !p.remove_center;
-    const size_t sm = tile_smem(p);
+    const bool k3 = p.P == 9;
+    const size_t sm = tile_smem(p, false);
     const unsigned grid = tile_grid(p);
 #define GP_BWD(LL, K3)                                                                                          \
     dcnv3_bwd_tile<T, VEC, LL, K3><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, \
@@ -170,11 +173,13 @@ static int forward_impl(const void *in, const void *off, const void *msk, void *
     if (int e = make_params(d, p)) return e;
     if (!aligned16(in) || !aligned16(off) || !aligned16(msk) || !aligned16(out)) return GP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
-    int L = 0;
-    if (plan_tiled(p, dtype, &L)) {
+    int L = 0, vec = 0;
+    if (plan_tiled(p, dtype, &L, &vec)) {
         if (dtype == GP_F32) launch_fwd_tile<float, 4, SOFTMAX>(in, off, msk, out, p, L, st);
-        else if (dtype == GP_BF16) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
-        else launch_fwd_tile<__half, 8, SOFTMAX>(in, off, msk, out, p, L, st);
+        else if (dtype == GP_BF16 && vec == 8) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
+        else if (dtype == GP_BF16) launch_fwd_tile<__nv_bfloat16, 4, SOFTMAX>(in, off, msk, out, p, L, st);
+        else if (vec == 8) launch_fwd_tile<__half, 8, SOFTMAX>(in, off, msk, out, p, L, st);
+        else launch_fwd_tile<__half, 4, SOFTMAX>(in, off, msk, out, p, L, st);
     } else {
         switch (dtype) {
             case GP_F32: launch_fwd_generic<float, SOFTMAX>(in, off, msk, out, p, st); break;
@@ -215,11 +220,12 @@ int gp_dcnv3_out_size(int size, int k, int stride, int pad, int dil) {
 uint64_t gp_launch_count(void) { return g_launches; }
 void gp_launch_count_reset(void) { g_launches = 0; }
 
-int gp_set_tuning(int tile_h, int tile_w, int gs) {
+int gp_set_tuning(int tile_h, int tile_w, int gs, int vec16) {
     init_tuning();
     if (tile_h > 0) g_tune.tile_h = tile_h;
     if (tile_w > 0) g_tune.tile_w = tile_w;
     if (gs > 0) g_tune.gs = gs;
+    if (vec16 == 4 || vec16 == 8) g_tune.vec16 = vec16;
     return GP_OK;
 }
 
@@ -270,11 +276,13 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
         if (ce != cudaSuccess) return (int)ce;
     }
 
-    int L = 0;
-    if (plan_tiled(p, dtype, &L)) {
+    int L = 0, vec = 0;
+    if (plan_tiled(p, dtype, &L, &vec)) {
         if (dtype == GP_F32) launch_bwd_tile<float, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else launch_bwd_tile<__half, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (dtype == GP_BF16 && vec == 8) launch_bwd_tile<__nv_bfloat16, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (vec == 8) launch_bwd_tile<__half, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else launch_bwd_tile<__half, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
     } else {
         switch (dtype) {
             case GP_F32: launch_bwd_generic<float>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;

@@ -9,15 +9,20 @@
 //   CTA       = a tile_h x tile_w patch of output pixels x `gs` groups of ONE image, so the input rows it
 //               gathers form a compact window that stays in L1 (channel-last rows of one group are
 //               contiguous: gc*sizeof(T) bytes = one 128-byte line for gc=32 fp32).
-//   staging   = the CTA's offset / mask rows are read once, coalesced, widened to fp32 (and, for the
-//               fused variant, soft-maxed over the P points) into shared memory; the sampling loop then
-//               reads them with conflict-free broadcast LDS.
-//   thread    = VEC channels (16 bytes) of one unit; L = gc/VEC consecutive lanes form a unit, so every
-//               corner gather of a unit is one fully-used 128-bit-per-lane coalesced request.
+//   records   = the CTA's offset / mask rows are read once, coalesced; ONE thread per (unit, point) turns
+//               them into a 24-byte sampling record in shared memory (corner-1 element offset, bounds
+//               flags, and either the four mask-folded bilinear weights (forward) or lh/lw/mask (backward);
+//               for the fused variant the softmax over the P points happens here).  The sampling loop reads
+//               a record with two conflict-free broadcast LDS and does no coordinate arithmetic at all:
+//               the kernels are bound by L1 wavefronts (one 128-byte line per corner per unit), so the
+//               instruction stream has to stay well under 4 issue slots per wavefront.
+//   thread    = VEC channels of one unit; L = gc/VEC consecutive lanes form a unit, so every corner
+//               gather of a unit is one fully-used coalesced request.
 //   backward  = same tiling; grad_input goes out as 16-byte vector reductions (REDG.ADD.F32x4) that
-//               resolve in L2 on the tile's window; the three per-point sums over the gc channels are
-//               butterfly-reduced with warp shuffles over the L lanes (no block barriers), parked in the
-//               staging buffer and written back coalesced.
+//               resolve in L2; grad_offset / grad_mask only need the four dot products
+//               d_k = sum_c top_grad[c]*corner_k[c], which are combined per lane and summed over the L lanes
+//               of the unit with a transposing butterfly (log2(L)+1 shuffles, no block barriers), parked in
+//               the consumed record and written back coalesced.
 #pragma once
 
 #include "gp_common.cuh"
@@ -27,7 +32,7 @@ namespace gp {
 constexpr int kTileThreads = 256;
 
 // ---------------------------------------------------------------------------------------------------
-// CTA decode + staging shared by forward and backward
+// CTA decode + per-CTA sampling records shared by forward and backward
 // ---------------------------------------------------------------------------------------------------
 struct TileCtx {
     int b, oh0, ow0, g0, TP, n_ul;
@@ -50,120 +55,152 @@ __device__ __forceinline__ TileCtx decode_tile(const KParams &p) {
     return t;
 }
 
-// smem layout: s_off[(ul*P + pt)*2 + {0,1}], s_msk[ul*P + pt], ul = g_local*TP + pix  (group-major so that
-// consecutive passes of the sampling loop work on one group => one L1-resident window at a time)
-template <typename T, bool SOFTMAX>
-__device__ __forceinline__ void stage_offsets_mask(const T *__restrict__ off, const T *__restrict__ msk, float *s_off,
-                                                   float *s_msk, const KParams &p, const TileCtx &t) {
-    const int P = p.P;
-    const int row2 = p.gs * P * 2, row1 = p.gs * P;
-    for (int e = threadIdx.x; e < t.TP * row2; e += blockDim.x) {
-        const int pix = e / row2, r = e - pix * row2;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
-        float v = 0.f;
-        if (oh < p.Ho && ow < p.Wo) {
-            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            v = to_acc<T>(__ldg(off + (q * p.G + t.g0) * (long long)(P * 2) + r));
-        }
-        const int gl = r / (P * 2);
-        s_off[(gl * t.TP + pix) * (P * 2) + (r - gl * P * 2)] = v;
-    }
-    for (int e = threadIdx.x; e < t.TP * row1; e += blockDim.x) {
-        const int pix = e / row1, r = e - pix * row1;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
-        float v = 0.f;
-        if (oh < p.Ho && ow < p.Wo) {
-            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            v = to_acc<T>(__ldg(msk + (q * p.G + t.g0) * (long long)P + r));
-        }
-        const int gl = r / P;
-        s_msk[(gl * t.TP + pix) * P + (r - gl * P)] = v;
-    }
-    __syncthreads();
+constexpr unsigned F_ALL = 32u;   // all four corners inside the image (fast path: four unpredicated loads)
+
+// One record per (unit, point), built ONCE per CTA by one thread and then read (LDS broadcast) by the L lanes
+// that own the unit's channels, so the coordinate arithmetic (locate(), the same device function the index
+// hook runs) is not repeated per channel as in the reference kernel (cuh:249-269 run by every thread).
+//   s_bf[r] = { BYTE offset of corner 1 relative to (image, group), flags }      flags == 0: out of range
+//   s_w [r] = forward : { w1, w2, w3, w4 } * mask, 0 for corners outside the image
+//             backward: { lh, lw, mask, - }; after the unit is processed { grad_off_w, grad_off_h, grad_mask, - }
+// r = ul*P + pt with ul = g_local*TP + pix (group-major: consecutive passes work on one group's window).
+// smem: n_rec * 24 bytes (+ 8 bytes per unit for the fused softmax).
+template <typename T, bool SOFTMAX, bool BWD>
+__device__ __forceinline__ void build_records(const T *__restrict__ off, const T *__restrict__ msk, float4 *s_w,
+                                              int2 *s_bf, float *s_red, const KParams &p, const TileCtx &t) {
+    const int P = p.P, rowP = p.gs * P;
     if (SOFTMAX) {   // softmax over the P logits of each (pixel, group) row: modules/dcnv3.py:332-333
         for (int ul = threadIdx.x; ul < t.n_ul; ul += blockDim.x) {
-            float *row = s_msk + ul * P;
-            float mx = row[0];
-            for (int i = 1; i < P; ++i) mx = fmaxf(mx, row[i]);
-            float sum = 0.f;
-            for (int i = 0; i < P; ++i) {
-                const float e = expf(row[i] - mx);
-                row[i] = e;
-                sum += e;
+            const int gl = ul / t.TP, pix = ul - gl * t.TP;
+            const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
+            float mx = 0.f, inv = 0.f;
+            if (oh < p.Ho && ow < p.Wo) {
+                const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
+                const T *row = msk + (q * p.G + t.g0 + gl) * (long long)P;
+                mx = to_acc<T>(row[0]);
+                for (int i = 1; i < P; ++i) mx = fmaxf(mx, to_acc<T>(row[i]));
+                float sum = 0.f;
+                for (int i = 0; i < P; ++i) sum += expf(to_acc<T>(row[i]) - mx);
+                inv = 1.f / sum;
             }
-            const float inv = 1.f / sum;
-            for (int i = 0; i < P; ++i) row[i] *= inv;
+            s_red[2 * ul] = mx;
+            s_red[2 * ul + 1] = inv;
         }
         __syncthreads();
+    }
+    const int cidx = (p.kw / 2) * p.kh + p.kh / 2;   // the centre point in the full kw*kh enumeration
+    const int C = p.C, WC = p.W * C;
+    for (int e = threadIdx.x; e < t.TP * rowP; e += blockDim.x) {
+        const int pix = e / rowP, r = e - pix * rowP;   // r = g_local*P + pt: global-memory order within a pixel row
+        const int gl = r / P, pt = r - gl * P;
+        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
+        const int ul = gl * t.TP + pix;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        int2 bf = make_int2(0, 0);
+        if (oh < p.Ho && ow < p.Wo) {
+            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
+            const long long k = (q * p.G + t.g0) * (long long)P + r;   // (q*G+g)*P + pt, cuh:243-244
+            float ox, oy;
+            load_pair<T>(off + 2 * k, ox, oy);   // (w, h) pair, cuh:261-262
+            float m = to_acc<T>(__ldg(msk + k));
+            if (SOFTMAX) m = expf(m - s_red[2 * ul]) * s_red[2 * ul + 1];
+            int kk = pt;
+            if (p.remove_center && kk >= cidx) ++kk;
+            const int i = kk / p.kh, j = kk - i * p.kh;   // p = i*kh + j, kernel WIDTH index i is the slow one (cuh:257-258)
+            const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
+            const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
+            Point<float> s;
+            locate<float>(s, p0_h_, p0_w_, j * p.dh, i * p.dw, ox, oy, p.scale, p.H, p.W);
+            if (s.flags & F_IN) {
+                bf.x = (s.h_low * WC + s.w_low * C) * (int)sizeof(T);
+                bf.y = (int)(s.flags | ((s.flags & 30u) == 30u ? F_ALL : 0u));
+                if (BWD) {
+                    w = make_float4(s.lh, s.lw, m, 0.f);
+                } else {   // cuh:76 weights, mask folded in; corners outside the image contribute 0 (cuh:55-75)
+                    w.x = (s.flags & F_C1) ? s.hh * s.hw * m : 0.f;
+                    w.y = (s.flags & F_C2) ? s.hh * s.lw * m : 0.f;
+                    w.z = (s.flags & F_C3) ? s.lh * s.hw * m : 0.f;
+                    w.w = (s.flags & F_C4) ? s.lh * s.lw * m : 0.f;
+                }
+            }
+        }
+        s_w[ul * P + pt] = w;
+        s_bf[ul * P + pt] = bf;
+    }
+    __syncthreads();
+}
+
+// the four corner loads of one sampling point; corners outside the image read nothing and count as 0
+// (addresses are byte pointers + 32-bit byte strides: two integer instructions per corner)
+template <typename T, int VEC>
+__device__ __forceinline__ void gather4(const char *p1, int Cb, int WCb, unsigned flags, float (&v1)[VEC],
+                                        float (&v2)[VEC], float (&v3)[VEC], float (&v4)[VEC]) {
+    const char *p3 = p1 + WCb;
+    if (flags & F_ALL) {
+        Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
+        Vec<T, VEC>::load(reinterpret_cast<const T *>(p1 + Cb), v2);
+        Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
+        Vec<T, VEC>::load(reinterpret_cast<const T *>(p3 + Cb), v4);
+    } else {
+#pragma unroll
+        for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
+        if (flags & F_C1) Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
+        if (flags & F_C2) Vec<T, VEC>::load(reinterpret_cast<const T *>(p1 + Cb), v2);
+        if (flags & F_C3) Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
+        if (flags & F_C4) Vec<T, VEC>::load(reinterpret_cast<const T *>(p3 + Cb), v4);
     }
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Forward, tiled + vectorised.  K3 = 3x3 kernel without remove_center (fully unrolled).
+// Forward, tiled + vectorised.  P9 = 9 sampling points (3x3 without remove_center), fully unrolled.
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L, bool K3, bool SOFTMAX>
+template <typename T, int VEC, int L, bool P9, bool SOFTMAX>
 __global__ void __launch_bounds__(kTileThreads)
 dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ msk, T *__restrict__ out,
                const __grid_constant__ KParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ float4 smem4[];
     const TileCtx t = decode_tile(p);
-    const int P = p.P;
-    float *s_off = smem, *s_msk = smem + t.n_ul * P * 2;
-    stage_offsets_mask<T, SOFTMAX>(off, msk, s_off, s_msk, p, t);
+    const int P = P9 ? 9 : p.P;
+    const int n_rec = t.n_ul * P;
+    float4 *s_w = smem4;
+    int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
+    float *s_red = reinterpret_cast<float *>(s_bf + n_rec);
+    build_records<T, SOFTMAX, false>(off, msk, s_w, s_bf, s_red, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;
+    const int Cb = C * (int)sizeof(T), WCb = WC * (int)sizeof(T);
     const T *in_b = in + (long long)t.b * p.H * WC + cl * VEC;
+    constexpr int UPB = kTileThreads / L;   // units per pass
 
-    for (int ul = threadIdx.x / L; ul < t.n_ul; ul += kTileThreads / L) {
+    for (int ul = threadIdx.x / L; ul < t.n_ul; ul += UPB) {
         const int gl = ul / t.TP, pix = ul - gl * t.TP;
         const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
         if (oh >= p.Ho || ow >= p.Wo) continue;
         const int g = t.g0 + gl;
-        const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
-        const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
-        const T *in_g = in_b + g * p.gc;
-        const float2 *so = reinterpret_cast<const float2 *>(s_off) + ul * P;
-        const float *sm = s_msk + ul * P;
+        const char *in_g = reinterpret_cast<const char *>(in_b + g * p.gc);
+        const float4 *rw = s_w + ul * P;
+        const int2 *rb = s_bf + ul * P;
 
         float acc[VEC];
 #pragma unroll
         for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
 
-        auto sample = [&](int i, int j, int pt_idx) {
-            const float2 o = so[pt_idx];
-            const float m = sm[pt_idx];
-            Point<float> pt;
-            locate<float>(pt, p0_h_, p0_w_, j * p.dh, i * p.dw, o.x, o.y, p.scale, p.H, p.W);
-            if (pt.flags & F_IN) {
-                const int base = pt.h_low * WC + pt.w_low * C;
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+        auto sample = [&](int k) {
+            const int2 bf = rb[k];
+            if (bf.y == 0) return;   // sample out of range: contributes nothing (cuh:268-269)
+            const float4 w = rw[k];
+            float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+            gather4<T, VEC>(in_g + bf.x, Cb, WCb, (unsigned)bf.y, v1, v2, v3, v4);
 #pragma unroll
-                for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
-                if (pt.flags & F_C1) Vec<T, VEC>::load(in_g + base, v1);
-                if (pt.flags & F_C2) Vec<T, VEC>::load(in_g + base + C, v2);
-                if (pt.flags & F_C3) Vec<T, VEC>::load(in_g + base + WC, v3);
-                if (pt.flags & F_C4) Vec<T, VEC>::load(in_g + base + WC + C, v4);
-                const float w1 = pt.hh * pt.hw, w2 = pt.hh * pt.lw, w3 = pt.lh * pt.hw, w4 = pt.lh * pt.lw;
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) {
-                    const float val = (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]);   // cuh:78
-                    acc[c] += val * m;                                                        // cuh:270-273
-                }
-            }
+            for (int c = 0; c < VEC; ++c)   // (w1 v1 + w2 v2 + w3 v3 + w4 v4) * mask, cuh:78 + :270-273
+                acc[c] = fmaf(w.x, v1[c], fmaf(w.y, v2[c], fmaf(w.z, v3[c], fmaf(w.w, v4[c], acc[c]))));
         };
-
-        if (K3) {
+        if (P9) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) sample(i, j, i * 3 + j);
+            for (int k = 0; k < 9; ++k) sample(k);
         } else {
-            const int ch = p.kh / 2, cw = p.kw / 2;
-            int pt_idx = 0;
-            for (int i = 0; i < p.kw; ++i)
-                for (int j = 0; j < p.kh; ++j)
-                    if (i != cw || j != ch || !p.remove_center) sample(i, j, pt_idx++);
+            for (int k = 0; k < P; ++k) sample(k);
         }
         const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
         Vec<T, VEC>::store_stream(out + q * C + g * p.gc + cl * VEC, acc);
@@ -232,39 +269,69 @@ dcnv3_fwd_generic(const T *__restrict__ in, const T *__restrict__ off, const T *
 // Backward, tiled + vectorised.  gin accumulates in fp32 (grad_input itself for T=float, the workspace
 // for 16-bit storage -- the reference does the same for half, dcnv3_cuda.cu:126-133).
 // ---------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int L, bool K3>
+
+// Sum (a, b, c) over the L lanes of a unit with a transposing butterfly: log2(L)+1 shuffles instead of
+// 3*log2(L).  On return lane 0 of the unit holds sum(a), lane 2 (L>=4; lane 0 for L==2) sum(b), lane 1 sum(c).
+template <int L>
+__device__ __forceinline__ void unit_reduce3(float &a, float &b, float &c, int cl) {
+    if (L == 1) return;
+    const unsigned full = 0xffffffffu;
+    const bool odd = cl & 1;
+    // xor 1: even lanes keep (a, b), odd lanes keep (c, -)
+    const float x = __shfl_xor_sync(full, odd ? a : c, 1);
+    const float y = __shfl_xor_sync(full, b, 1);
+    float p0 = odd ? c + x : a + x;   // even: a, odd: c
+    float p1 = b + y;                 // even: b (odd lanes' copy is unused)
+    if (L >= 4) {
+        // xor 2: among even lanes bit1==0 keeps a, bit1==1 keeps b; odd lanes keep c
+        const bool hi = cl & 2;
+        const float z = __shfl_xor_sync(full, (hi || odd) ? p0 : p1, 2);
+        p0 = (hi && !odd) ? p1 + z : p0 + z;
+#pragma unroll
+        for (int o = 4; o < L; o <<= 1) p0 += __shfl_xor_sync(full, p0, o);
+        a = b = c = p0;   // lane 0: a, lane 2: b, lane 1: c
+    } else {
+        a = p0;   // lane 0: a, lane 1: c
+        b = p1;   // lane 0: b
+        c = p0;
+    }
+}
+
+template <typename T, int VEC, int L, bool P9>
 __global__ void __launch_bounds__(kTileThreads)
 dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ msk,
                const T *__restrict__ gout, float *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmsk,
                const __grid_constant__ KParams p) {
-    extern __shared__ float smem[];
+    extern __shared__ float4 smem4[];
     const TileCtx t = decode_tile(p);
-    const int P = p.P;
-    float *s_off = smem, *s_msk = smem + t.n_ul * P * 2;
-    stage_offsets_mask<T, false>(off, msk, s_off, s_msk, p, t);
+    const int P = P9 ? 9 : p.P;
+    const int n_rec = t.n_ul * P;
+    float4 *s_w = smem4;
+    int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
+    build_records<T, false, true>(off, msk, s_w, s_bf, nullptr, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;
+    const int Cb = C * (int)sizeof(T), WCb = WC * (int)sizeof(T);
+    constexpr int GS = (int)(sizeof(float) / sizeof(T));   // byte-offset scale from T storage to the fp32 accumulation image
     const long long img = (long long)t.b * p.H * WC;
     const T *in_b = in + img + cl * VEC;
     float *gin_b = gin + img + cl * VEC;
-    const int n_pass = (t.n_ul + kTileThreads / L - 1) / (kTileThreads / L);
+    constexpr int UPB = kTileThreads / L;
+    const int n_pass = (t.n_ul + UPB - 1) / UPB;
 
     for (int pass = 0; pass < n_pass; ++pass) {
-        const int ul = pass * (kTileThreads / L) + threadIdx.x / L;
+        const int ul = pass * UPB + threadIdx.x / L;
         const int gl = ul / t.TP, pix = ul - gl * t.TP;
         const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
         const bool valid = ul < t.n_ul && oh < p.Ho && ow < p.Wo;
         if (!__any_sync(0xffffffffu, valid)) continue;   // warp-uniform
-        const int g = t.g0 + (valid ? gl : 0);
-        const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
-        const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
-        const T *in_g = in_b + g * p.gc;
-        float *gin_g = gin_b + g * p.gc;
         const int ulc = valid ? ul : 0;
-        float2 *so = reinterpret_cast<float2 *>(s_off) + ulc * P;
-        float *sm = s_msk + ulc * P;
-        const int Hv = valid ? p.H : 0;   // invalid lanes: every sample out of range => no memory traffic
+        const int g = t.g0 + (valid ? gl : 0);
+        const char *in_g = reinterpret_cast<const char *>(in_b + g * p.gc);
+        char *gin_g = reinterpret_cast<char *>(gin_b + g * p.gc);
+        float4 *rw = s_w + ulc * P;
+        const int2 *rb = s_bf + ulc * P;
 
         float go[VEC];
 #pragma unroll
@@ -274,91 +341,77 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
             Vec<T, VEC>::load_stream(gout + q * C + g * p.gc + cl * VEC, go);
         }
 
-        auto sample = [&](int i, int j, int pt_idx) {
-            const float2 o = so[pt_idx];
-            const float m = sm[pt_idx];
-            Point<float> pt;
-            locate<float>(pt, p0_h_, p0_w_, j * p.dh, i * p.dw, o.x, o.y, p.scale, Hv, p.W);
-            float s_m = 0.f, s_w = 0.f, s_h = 0.f;
-            if (pt.flags & F_IN) {
-                const int base = pt.h_low * WC + pt.w_low * C;
+        auto sample = [&](int k) {
+            const int2 bf = rb[k];
+            const unsigned flags = valid ? (unsigned)bf.y : 0u;
+            float s_m = 0.f, s_w_ = 0.f, s_h = 0.f;
+            if (flags) {
+                const float4 r = rw[k];
+                const float lh = r.x, lw = r.y, m = r.z;
+                const float hh = 1.f - lh, hw = 1.f - lw;
+                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
                 float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-#pragma unroll
-                for (int c = 0; c < VEC; ++c) v1[c] = v2[c] = v3[c] = v4[c] = 0.f;
-                if (pt.flags & F_C1) Vec<T, VEC>::load(in_g + base, v1);
-                if (pt.flags & F_C2) Vec<T, VEC>::load(in_g + base + C, v2);
-                if (pt.flags & F_C3) Vec<T, VEC>::load(in_g + base + WC, v3);
-                if (pt.flags & F_C4) Vec<T, VEC>::load(in_g + base + WC + C, v4);
-                const float w1 = pt.hh * pt.hw, w2 = pt.hh * pt.lw, w3 = pt.lh * pt.hw, w4 = pt.lh * pt.lw;
-                float tg[VEC];   // top_grad * mask, cuh:107
+                gather4<T, VEC>(in_g + bf.x, Cb, WCb, flags, v1, v2, v3, v4);
+                // d_k = sum_c top_grad[c] * v_k[c]: everything grad_offset / grad_mask need (cuh:107-146 are linear in v_k)
+                float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
 #pragma unroll
                 for (int c = 0; c < VEC; ++c) {
-                    tg[c] = go[c] * m;
-                    const float val = (w1 * v1[c] + w2 * v2[c] + w3 * v3[c] + w4 * v4[c]);
-                    // grad_w_weight / grad_h_weight, cuh:114-139
-                    const float gw = pt.hh * (v2[c] - v1[c]) + pt.lh * (v4[c] - v3[c]);
-                    const float gh = pt.hw * (v3[c] - v1[c]) + pt.lw * (v4[c] - v2[c]);
-                    s_m += go[c] * val;       // cuh:144
-                    s_w += gw * tg[c];        // cuh:145 (offset_scale applied after the channel sum)
-                    s_h += gh * tg[c];        // cuh:146
+                    d1 = fmaf(go[c], v1[c], d1);
+                    d2 = fmaf(go[c], v2[c], d2);
+                    d3 = fmaf(go[c], v3[c], d3);
+                    d4 = fmaf(go[c], v4[c], d4);
                 }
-                if (!(p.debug & 1))
+                s_m = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;                  // cuh:144  sum_c top_grad * val
+                s_w_ = m * (hh * (d2 - d1) + lh * (d4 - d3));                 // cuh:145  grad_w_weight * top_grad * mask
+                s_h = m * (hw * (d3 - d1) + lw * (d4 - d2));                  // cuh:146  grad_h_weight * top_grad * mask
+                // cuh:116-140: grad_im[corner] += w_corner * top_grad * mask, one 16-byte reduction per corner
+                const float m1 = w1 * m, m2 = w2 * m, m3 = w3 * m, m4 = w4 * m;
+                char *g1 = gin_g + bf.x * GS, *g3 = g1 + WCb * GS;
 #pragma unroll
-                for (int c4 = 0; c4 < VEC; c4 += 4) {   // cuh:116-140: one 16-byte reduction per corner
-                    if (pt.flags & F_C1) red_add_v4(gin_g + base + c4, w1 * tg[c4], w1 * tg[c4 + 1], w1 * tg[c4 + 2], w1 * tg[c4 + 3]);
-                    if (pt.flags & F_C2) red_add_v4(gin_g + base + C + c4, w2 * tg[c4], w2 * tg[c4 + 1], w2 * tg[c4 + 2], w2 * tg[c4 + 3]);
-                    if (pt.flags & F_C3) red_add_v4(gin_g + base + WC + c4, w3 * tg[c4], w3 * tg[c4 + 1], w3 * tg[c4 + 2], w3 * tg[c4 + 3]);
-                    if (pt.flags & F_C4) red_add_v4(gin_g + base + WC + C + c4, w4 * tg[c4], w4 * tg[c4 + 1], w4 * tg[c4 + 2], w4 * tg[c4 + 3]);
+                for (int c4 = 0; c4 < VEC; c4 += 4) {
+                    if (flags & F_C1) red_add_v4(reinterpret_cast<float *>(g1) + c4, m1 * go[c4], m1 * go[c4 + 1], m1 * go[c4 + 2], m1 * go[c4 + 3]);
+                    if (flags & F_C2) red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, m2 * go[c4], m2 * go[c4 + 1], m2 * go[c4 + 2], m2 * go[c4 + 3]);
+                    if (flags & F_C3) red_add_v4(reinterpret_cast<float *>(g3) + c4, m3 * go[c4], m3 * go[c4 + 1], m3 * go[c4 + 2], m3 * go[c4 + 3]);
+                    if (flags & F_C4) red_add_v4(reinterpret_cast<float *>(g3 + Cb * GS) + c4, m4 * go[c4], m4 * go[c4 + 1], m4 * go[c4 + 2], m4 * go[c4 + 3]);
                 }
             }
-            // sum over the gc channels of the group = butterfly over the L lanes of this unit
-            if (!(p.debug & 2))
-#pragma unroll
-            for (int o2 = L / 2; o2 > 0; o2 >>= 1) {
-                s_m += __shfl_xor_sync(0xffffffffu, s_m, o2);
-                s_w += __shfl_xor_sync(0xffffffffu, s_w, o2);
-                s_h += __shfl_xor_sync(0xffffffffu, s_h, o2);
-            }
-            if (cl == 0 && valid) {   // park the results in the (now consumed) staging slots
-                so[pt_idx] = make_float2(p.scale * s_w, p.scale * s_h);
-                sm[pt_idx] = s_m;
+            // sum over the gc channels of the group = reduction over the L lanes of this unit (no block barriers)
+            unit_reduce3<L>(s_m, s_w_, s_h, cl);
+            if (valid) {   // park the results in the (now consumed) record
+                float *slot = reinterpret_cast<float *>(rw + k);
+                if (L == 1) {
+                    slot[0] = p.scale * s_w_; slot[1] = p.scale * s_h; slot[2] = s_m;
+                } else if (L == 2) {
+                    if (cl == 0) { slot[2] = s_m; slot[0] = p.scale * s_w_; } else { slot[1] = p.scale * s_h; }
+                } else {
+                    if (cl == 0) slot[2] = s_m;
+                    else if (cl == 2) slot[0] = p.scale * s_w_;
+                    else if (cl == 1) slot[1] = p.scale * s_h;
+                }
             }
         };
-
-        if (K3) {
+        if (P9) {
 #pragma unroll
-            for (int i = 0; i < 3; ++i)
-#pragma unroll
-                for (int j = 0; j < 3; ++j) sample(i, j, i * 3 + j);
+            for (int k = 0; k < 9; ++k) sample(k);
         } else {
-            const int ch = p.kh / 2, cw = p.kw / 2;
-            int pt_idx = 0;
-            for (int i = 0; i < p.kw; ++i)
-                for (int j = 0; j < p.kh; ++j)
-                    if (i != cw || j != ch || !p.remove_center) sample(i, j, pt_idx++);
+            for (int k = 0; k < P; ++k) sample(k);
         }
     }
     __syncthreads();
 
-    // coalesced write-back of grad_offset / grad_mask (inverse of the staging permutation)
-    const int row2 = p.gs * P * 2, row1 = p.gs * P;
-    for (int e = threadIdx.x; e < t.TP * row2; e += blockDim.x) {
-        const int pix = e / row2, r = e - pix * row2;
+    // coalesced write-back of grad_offset / grad_mask in global-memory order (inverse of the record permutation)
+    const int rowP = p.gs * P;
+    for (int e = threadIdx.x; e < t.TP * rowP; e += blockDim.x) {
+        const int pix = e / rowP, r = e - pix * rowP;
+        const int gl = r / P, pt = r - gl * P;
         const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
         if (oh < p.Ho && ow < p.Wo) {
             const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            const int gl = r / (P * 2);
-            goff[(q * p.G + t.g0) * (long long)(P * 2) + r] =
-                from_acc<T, float>(s_off[(gl * t.TP + pix) * (P * 2) + (r - gl * P * 2)]);
-        }
-    }
-    for (int e = threadIdx.x; e < t.TP * row1; e += blockDim.x) {
-        const int pix = e / row1, r = e - pix * row1;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
-        if (oh < p.Ho && ow < p.Wo) {
-            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            const int gl = r / P;
-            gmsk[(q * p.G + t.g0) * (long long)P + r] = from_acc<T, float>(s_msk[(gl * t.TP + pix) * P + (r - gl * P)]);
+            const long long k = (q * p.G + t.g0) * (long long)P + r;
+            const int rec = (gl * t.TP + pix) * P + pt;
+            const float4 res = s_w[rec];   // out-of-range samples parked 0, 0, 0 (cuh:347-355)
+            store_pair<T>(goff + 2 * k, res.x, res.y);
+            gmsk[k] = from_acc<T, float>(res.z);
         }
     }
 }

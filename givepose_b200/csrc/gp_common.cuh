@@ -30,7 +30,6 @@ struct KParams {
     // tiling of the output plane used by the tiled kernels
     int tile_h, tile_w, tiles_y, tiles_x, gs /*groups per CTA*/, gchunks /*G/gs*/;
     long long n_units;       // N*Ho*Wo*G
-    int debug;               // profiling only (GP_DEBUG env): bit0 skip grad_input reductions, bit1 skip lane reductions
 };
 
 template <typename T> struct AccOf { using type = float; };
@@ -169,6 +168,75 @@ template <> struct Vec<__half, 8> {
         asm volatile("st.global.cs.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]) : "memory");
     }
 };
+
+// 16-bit storage, 4 channels per lane (8-byte requests): same L1 wavefront count per unit as the 8-channel
+// variant, half the registers / instructions per lane
+template <> struct Vec<__nv_bfloat16, 4> {
+    static __device__ __forceinline__ void unpack(const uint2 r, float (&v)[4]) {
+        v[0] = __uint_as_float(r.x << 16); v[1] = __uint_as_float(r.x & 0xffff0000u);
+        v[2] = __uint_as_float(r.y << 16); v[3] = __uint_as_float(r.y & 0xffff0000u);
+    }
+    static __device__ __forceinline__ void load(const __nv_bfloat16 *p, float (&v)[4]) {
+        unpack(__ldg(reinterpret_cast<const uint2 *>(p)), v);
+    }
+    static __device__ __forceinline__ void load_stream(const __nv_bfloat16 *p, float (&v)[4]) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        unpack(r, v);
+    }
+    static __device__ __forceinline__ void store_stream(__nv_bfloat16 *p, const float (&v)[4]) {
+        const __nv_bfloat162 a = __floats2bfloat162_rn(v[0], v[1]), b = __floats2bfloat162_rn(v[2], v[3]);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t *>(&a)),
+                     "r"(*reinterpret_cast<const uint32_t *>(&b)) : "memory");
+    }
+};
+
+template <> struct Vec<__half, 4> {
+    static __device__ __forceinline__ void unpack(const uint2 r, float (&v)[4]) {
+        const float2 a = __half22float2(*reinterpret_cast<const __half2 *>(&r.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2 *>(&r.y));
+        v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+    }
+    static __device__ __forceinline__ void load(const __half *p, float (&v)[4]) {
+        unpack(__ldg(reinterpret_cast<const uint2 *>(p)), v);
+    }
+    static __device__ __forceinline__ void load_stream(const __half *p, float (&v)[4]) {
+        uint2 r;
+        asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+        unpack(r, v);
+    }
+    static __device__ __forceinline__ void store_stream(__half *p, const float (&v)[4]) {
+        const __half2 a = __floats2half2_rn(v[0], v[1]), b = __floats2half2_rn(v[2], v[3]);
+        asm volatile("st.global.cs.v2.u32 [%0], {%1,%2};" ::"l"(p), "r"(*reinterpret_cast<const uint32_t *>(&a)),
+                     "r"(*reinterpret_cast<const uint32_t *>(&b)) : "memory");
+    }
+};
+
+// (x, y) pair of consecutive elements, e.g. one sampling point's (w, h) offset
+template <typename T> __device__ __forceinline__ void load_pair(const T *p, float &a, float &b);
+template <> __device__ __forceinline__ void load_pair<float>(const float *p, float &a, float &b) {
+    const float2 r = __ldg(reinterpret_cast<const float2 *>(p));
+    a = r.x; b = r.y;
+}
+template <> __device__ __forceinline__ void load_pair<__nv_bfloat16>(const __nv_bfloat16 *p, float &a, float &b) {
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+    a = __uint_as_float(r << 16); b = __uint_as_float(r & 0xffff0000u);
+}
+template <> __device__ __forceinline__ void load_pair<__half>(const __half *p, float &a, float &b) {
+    const uint32_t r = __ldg(reinterpret_cast<const uint32_t *>(p));
+    const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&r));
+    a = f.x; b = f.y;
+}
+template <typename T> __device__ __forceinline__ void store_pair(T *p, float a, float b);
+template <> __device__ __forceinline__ void store_pair<float>(float *p, float a, float b) {
+    *reinterpret_cast<float2 *>(p) = make_float2(a, b);
+}
+template <> __device__ __forceinline__ void store_pair<__nv_bfloat16>(__nv_bfloat16 *p, float a, float b) {
+    *reinterpret_cast<__nv_bfloat162 *>(p) = __floats2bfloat162_rn(a, b);
+}
+template <> __device__ __forceinline__ void store_pair<__half>(__half *p, float a, float b) {
+    *reinterpret_cast<__half2 *>(p) = __floats2half2_rn(a, b);
+}
 
 // fp32 vector reduction into global memory (REDG.E.ADD.F32x4 on sm_90+): one 16-byte atomic per lane
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {

@@ -51,8 +51,8 @@ def main():
     ap.add_argument("--quick", action="store_true")
     a = ap.parse_args()
     shapes = [("K_N64", 64, 64, 64, 8, 32, 1, False), ("M_64to32_N256", 256, 64, 64, 4, 64, 2, True)]
-    tiles = [(8, 8, 1), (8, 8, 2), (8, 8, 4), (4, 16, 1), (16, 16, 1), (8, 16, 1), (4, 8, 1), (4, 4, 1), (16, 8, 2),
-             (2, 32, 1), (8, 32, 1)]
+    tiles = [(8, 8, 1), (8, 8, 2), (8, 8, 4), (4, 16, 1), (8, 16, 1), (4, 8, 1), (4, 4, 1), (4, 4, 2), (4, 4, 4), (4, 4, 8),
+             (2, 32, 1), (4, 8, 2), (4, 8, 4)]
     if a.quick:
         tiles = tiles[:3]
     rows = []
@@ -63,12 +63,13 @@ def main():
                 args = (3, 3, s, s, 1, 1, 1, 1, G, gc, 1.0)
                 fb, bb = alg_bytes(N, H, W, G * gc, G, 9, Ho, Wo, inp.element_size())
                 for th, tw, gs in tiles:
+                  for vec16 in ((8, 4) if dn == "bf16" else (8,)):
                     if G % gs:
                         continue
-                    lib.gp_set_tuning(th, tw, gs)
+                    lib.gp_set_tuning(th, tw, gs, vec16)
                     tf = timeit(lambda: F.dcnv3_forward(inp, off, m, *args, 256, 0))
                     tb = timeit(lambda: F.dcnv3_backward(inp, off, m, *args, gout, 256, 0))
-                    row = dict(shape=name, dtype=dn, dist=dist, tile=(th, tw, gs), fwd_ms=round(tf, 4), bwd_ms=round(tb, 4),
+                    row = dict(shape=name, dtype=dn, dist=dist, tile=(th, tw, gs), vec16=vec16, fwd_ms=round(tf, 4), bwd_ms=round(tb, 4),
                                fwd_GBps=round(fb / tf / 1e6, 1), bwd_GBps=round(bb / tb / 1e6, 1),
                                fwdbwd_GBps=round((fb + bb) / (tf + tb) / 1e6, 1))
                     rows.append(row)
