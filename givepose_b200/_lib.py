@@ -10,7 +10,7 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libgivepose_b200.so")
+LIB_PATH = os.environ.get("GIVEPOSE_B200_LIB") or os.path.join(_HERE, "lib", "libgivepose_b200.so")   # override: tuning builds only
 CSRC = os.path.join(_HERE, "csrc")
 
 GP_F32, GP_BF16, GP_F16, GP_F64 = 0, 1, 2, 3

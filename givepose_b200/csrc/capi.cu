@@ -12,8 +12,9 @@ namespace gp {
 unsigned long long g_launches = 0;
 
 struct Tuning {
-    int tile_h = 8, tile_w = 8, gs = 1;
-    int vec16 = 8;   // channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
+    int tile_h = 8, tile_w = 8, gs = 2;   // measured best on B200 (profiles/r01_sweep.md)
+    int vec16 = 8;   // forward: channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
+                     // backward always uses 4: its fp32 reductions then cover whole 128-byte lines per request
     bool init = false;
 };
 static Tuning g_tune;
@@ -65,26 +66,29 @@ static size_t elem_size(int dtype) {
 static bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // can the tiled/vectorised kernels take this call?  fills the tiling fields of p.
-static bool plan_tiled(KParams &p, int dtype, int *L_out, int *vec_out) {
+static bool plan_tiled(KParams &p, int dtype, int *L_out, int *vec_out, bool backward = false) {
     if (dtype == GP_F64) return false;
     init_tuning();
-    int vec = dtype == GP_F32 ? 4 : g_tune.vec16;
+    int vec = dtype == GP_F32 ? 4 : (backward && p.gc % 4 == 0 && p.gc / 4 <= 32 ? 4 : g_tune.vec16);
     if (vec == 8 && (p.gc % 8 || p.gc / 8 > 32) && p.gc % 4 == 0) vec = 4;
     if (p.gc % vec) return false;
     const int L = p.gc / vec;
     if (L > 32 || (L & (L - 1))) return false;
     if ((long long)p.H * p.W * p.C * 4 >= (1ll << 31)) return false;   // 32-bit byte offsets inside one image
     int th = g_tune.tile_h, tw = g_tune.tile_w, gs = g_tune.gs;
-    if (th < 1) th = 1;
-    if (tw < 1) tw = 1;
-    if (gs < 1) gs = 1;
-    while (gs > 1 && p.G % gs) --gs;
+    auto pow2_floor = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
+    auto lg2 = [](int v) { int r = 0; while ((1 << r) < v) ++r; return r; };
+    th = pow2_floor(th < 1 ? 1 : th);
+    tw = pow2_floor(tw < 1 ? 1 : tw);
+    gs = pow2_floor(gs < 1 ? 1 : gs);
+    while (gs > 1 && p.G % gs) gs /= 2;
     // keep the sampling records under 48 KB of shared memory
-    while ((long long)th * tw * gs * (p.P * 24 + 8) > 48 * 1024) {
-        if (gs > 1) { gs = 1; continue; }
-        if (th >= tw && th > 1) th = (th + 1) / 2; else if (tw > 1) tw = (tw + 1) / 2; else return false;
+    while ((long long)th * tw * gs * (p.P * 24 + 12) > 48 * 1024) {
+        if (gs > 1) { gs /= 2; continue; }
+        if (th >= tw && th > 1) th /= 2; else if (tw > 1) tw /= 2; else return false;
     }
     p.tile_h = th; p.tile_w = tw; p.gs = gs; p.gchunks = p.G / gs;
+    p.lg_tw = lg2(tw); p.lg_tp = lg2(th * tw); p.lg_gs = lg2(gs);
     p.tiles_y = (p.Ho + th - 1) / th;
     p.tiles_x = (p.Wo + tw - 1) / tw;
     const long long ctas = (long long)p.N * p.tiles_y * p.tiles_x * p.gchunks;
@@ -95,7 +99,7 @@ static bool plan_tiled(KParams &p, int dtype, int *L_out, int *vec_out) {
 }
 
 static size_t tile_smem(const KParams &p, bool softmax) {
-    return (size_t)p.tile_h * p.tile_w * p.gs * (p.P * 24 + (softmax ? 8 : 0));
+    return (size_t)p.tile_h * p.tile_w * p.gs * (p.P * 24 + 4 + (softmax ? 8 : 0));
 }
 static unsigned tile_grid(const KParams &p) { return (unsigned)((long long)p.N * p.tiles_y * p.tiles_x * p.gchunks); }
 
@@ -277,7 +281,7 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
     }
 
     int L = 0, vec = 0;
-    if (plan_tiled(p, dtype, &L, &vec)) {
+    if (plan_tiled(p, dtype, &L, &vec, true)) {
         if (dtype == GP_F32) launch_bwd_tile<float, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
         else if (dtype == GP_BF16 && vec == 8) launch_bwd_tile<__nv_bfloat16, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
         else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);

@@ -30,6 +30,10 @@
 namespace gp {
 
 constexpr int kTileThreads = 256;
+#ifndef GP_MIN_BLOCKS
+#define GP_MIN_BLOCKS 4
+#endif
+constexpr int kTileMinBlocks = GP_MIN_BLOCKS;   // CTAs per SM the tiled kernels are register-budgeted for
 
 // ---------------------------------------------------------------------------------------------------
 // CTA decode + per-CTA sampling records shared by forward and backward
@@ -37,6 +41,19 @@ constexpr int kTileThreads = 256;
 struct TileCtx {
     int b, oh0, ow0, g0, TP, n_ul;
 };
+
+// tile_h, tile_w and gs are powers of two (plan_tiled): unit / pixel decode is shifts and masks
+struct UnitPos {
+    int gl, pix, oh, ow;
+};
+__device__ __forceinline__ UnitPos unit_pos(int ul, const KParams &p, const TileCtx &t) {
+    UnitPos u;
+    u.gl = ul >> p.lg_tp;
+    u.pix = ul & (t.TP - 1);
+    u.oh = t.oh0 + (u.pix >> p.lg_tw);
+    u.ow = t.ow0 + (u.pix & (p.tile_w - 1));
+    return u;
+}
 
 __device__ __forceinline__ TileCtx decode_tile(const KParams &p) {
     TileCtx t;
@@ -65,18 +82,20 @@ constexpr unsigned F_ALL = 32u;   // all four corners inside the image (fast pat
 //             backward: { lh, lw, mask, - }; after the unit is processed { grad_off_w, grad_off_h, grad_mask, - }
 // r = ul*P + pt with ul = g_local*TP + pix (group-major: consecutive passes work on one group's window).
 // smem: n_rec * 24 bytes (+ 8 bytes per unit for the fused softmax).
-template <typename T, bool SOFTMAX, bool BWD>
+template <typename T, bool SOFTMAX, bool BWD, bool P9>
 __device__ __forceinline__ void build_records(const T *__restrict__ off, const T *__restrict__ msk, float4 *s_w,
-                                              int2 *s_bf, float *s_red, const KParams &p, const TileCtx &t) {
-    const int P = p.P, rowP = p.gs * P;
-    if (SOFTMAX) {   // softmax over the P logits of each (pixel, group) row: modules/dcnv3.py:332-333
-        for (int ul = threadIdx.x; ul < t.n_ul; ul += blockDim.x) {
-            const int gl = ul / t.TP, pix = ul - gl * t.TP;
-            const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
+                                              int2 *s_bf, unsigned *s_unit, float *s_red, const KParams &p,
+                                              const TileCtx &t) {
+    const int P = P9 ? 9 : p.P;
+    // s_unit[ul] != 0  <=>  every sampling point of the unit has all four corners inside the image
+    for (int ul = threadIdx.x; ul < t.n_ul; ul += blockDim.x) {
+        s_unit[ul] = 1u;
+        if (SOFTMAX) {   // softmax over the P logits of each (pixel, group) row: modules/dcnv3.py:332-333
+            const UnitPos u = unit_pos(ul, p, t);
             float mx = 0.f, inv = 0.f;
-            if (oh < p.Ho && ow < p.Wo) {
-                const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-                const T *row = msk + (q * p.G + t.g0 + gl) * (long long)P;
+            if (u.oh < p.Ho && u.ow < p.Wo) {
+                const long long q = ((long long)t.b * p.Ho + u.oh) * p.Wo + u.ow;
+                const T *row = msk + (q * p.G + t.g0 + u.gl) * (long long)P;
                 mx = to_acc<T>(row[0]);
                 for (int i = 1; i < P; ++i) mx = fmaxf(mx, to_acc<T>(row[i]));
                 float sum = 0.f;
@@ -86,27 +105,34 @@ __device__ __forceinline__ void build_records(const T *__restrict__ off, const T
             s_red[2 * ul] = mx;
             s_red[2 * ul + 1] = inv;
         }
-        __syncthreads();
     }
+    __syncthreads();
     const int cidx = (p.kw / 2) * p.kh + p.kh / 2;   // the centre point in the full kw*kh enumeration
     const int C = p.C, WC = p.W * C;
-    for (int e = threadIdx.x; e < t.TP * rowP; e += blockDim.x) {
-        const int pix = e / rowP, r = e - pix * rowP;   // r = g_local*P + pt: global-memory order within a pixel row
-        const int gl = r / P, pt = r - gl * P;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
+    const int n_rec = t.n_ul * P;
+    for (int e = threadIdx.x; e < n_rec; e += blockDim.x) {
+        // e enumerates (pix, g_local, pt) with pt fastest: global-memory order within a pixel row
+        const int pg = e / P, pt = e - pg * P;
+        const int pix = pg >> p.lg_gs, gl = pg & (p.gs - 1);
+        const int oh = t.oh0 + (pix >> p.lg_tw), ow = t.ow0 + (pix & (p.tile_w - 1));
         const int ul = gl * t.TP + pix;
         float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
         int2 bf = make_int2(0, 0);
         if (oh < p.Ho && ow < p.Wo) {
             const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            const long long k = (q * p.G + t.g0) * (long long)P + r;   // (q*G+g)*P + pt, cuh:243-244
+            const long long k = ((q * p.G + t.g0 + gl) * (long long)P) + pt;   // (q*G+g)*P + pt, cuh:243-244
             float ox, oy;
             load_pair<T>(off + 2 * k, ox, oy);   // (w, h) pair, cuh:261-262
             float m = to_acc<T>(__ldg(msk + k));
             if (SOFTMAX) m = expf(m - s_red[2 * ul]) * s_red[2 * ul + 1];
-            int kk = pt;
-            if (p.remove_center && kk >= cidx) ++kk;
-            const int i = kk / p.kh, j = kk - i * p.kh;   // p = i*kh + j, kernel WIDTH index i is the slow one (cuh:257-258)
+            int i, j;   // p = i*kh + j, kernel WIDTH index i is the slow one (cuh:257-258)
+            if (P9) {
+                i = pt / 3; j = pt - i * 3;
+            } else {
+                int kk = pt;
+                if (p.remove_center && kk >= cidx) ++kk;
+                i = kk / p.kh; j = kk - i * p.kh;
+            }
             const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
             const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
             Point<float> s;
@@ -124,6 +150,7 @@ __device__ __forceinline__ void build_records(const T *__restrict__ off, const T
                 }
             }
         }
+        if (!(bf.y & (int)F_ALL)) s_unit[ul] = 0u;   // benign race: every writer stores 0
         s_w[ul * P + pt] = w;
         s_bf[ul * P + pt] = bf;
     }
@@ -155,7 +182,7 @@ __device__ __forceinline__ void gather4(const char *p1, int Cb, int WCb, unsigne
 // Forward, tiled + vectorised.  P9 = 9 sampling points (3x3 without remove_center), fully unrolled.
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int VEC, int L, bool P9, bool SOFTMAX>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks)
 dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ msk, T *__restrict__ out,
                const __grid_constant__ KParams p) {
     extern __shared__ float4 smem4[];
@@ -164,8 +191,9 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const int n_rec = t.n_ul * P;
     float4 *s_w = smem4;
     int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
-    float *s_red = reinterpret_cast<float *>(s_bf + n_rec);
-    build_records<T, SOFTMAX, false>(off, msk, s_w, s_bf, s_red, p, t);
+    unsigned *s_unit = reinterpret_cast<unsigned *>(s_bf + n_rec);
+    float *s_red = reinterpret_cast<float *>(s_unit + t.n_ul);
+    build_records<T, SOFTMAX, false, P9>(off, msk, s_w, s_bf, s_unit, s_red, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;
@@ -173,11 +201,15 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const T *in_b = in + (long long)t.b * p.H * WC + cl * VEC;
     constexpr int UPB = kTileThreads / L;   // units per pass
 
-    for (int ul = threadIdx.x / L; ul < t.n_ul; ul += UPB) {
-        const int gl = ul / t.TP, pix = ul - gl * t.TP;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
-        if (oh >= p.Ho || ow >= p.Wo) continue;
-        const int g = t.g0 + gl;
+    const int n_pass = (t.n_ul + UPB - 1) / UPB;
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const int ul = pass * UPB + threadIdx.x / L;
+        const UnitPos u = unit_pos(ul, p, t);
+        const bool valid = ul < t.n_ul && u.oh < p.Ho && u.ow < p.Wo;
+        // one decision per warp: a mixed warp would otherwise run the branch-free and the careful loop back to back
+        const bool fast = P9 && __all_sync(0xffffffffu, valid && s_unit[valid ? ul : 0]);
+        if (!valid) continue;
+        const int g = t.g0 + u.gl;
         const char *in_g = reinterpret_cast<const char *>(in_b + g * p.gc);
         const float4 *rw = s_w + ul * P;
         const int2 *rb = s_bf + ul * P;
@@ -186,23 +218,38 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
         for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
 
-        auto sample = [&](int k) {
-            const int2 bf = rb[k];
-            if (bf.y == 0) return;   // sample out of range: contributes nothing (cuh:268-269)
-            const float4 w = rw[k];
-            float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-            gather4<T, VEC>(in_g + bf.x, Cb, WCb, (unsigned)bf.y, v1, v2, v3, v4);
+        // (w1 v1 + w2 v2 + w3 v3 + w4 v4) * mask, cuh:78 + :270-273 (mask folded into the record's weights)
+        auto accumulate = [&](const float4 w, const float (&v1)[VEC], const float (&v2)[VEC], const float (&v3)[VEC],
+                              const float (&v4)[VEC]) {
 #pragma unroll
-            for (int c = 0; c < VEC; ++c)   // (w1 v1 + w2 v2 + w3 v3 + w4 v4) * mask, cuh:78 + :270-273
+            for (int c = 0; c < VEC; ++c)
                 acc[c] = fmaf(w.x, v1[c], fmaf(w.y, v2[c], fmaf(w.z, v3[c], fmaf(w.w, v4[c], acc[c]))));
         };
-        if (P9) {
+
+        if (fast) {
+            // interior unit: 36 unconditional gathers, no branches -> the scheduler overlaps points freely
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sample(k);
+            for (int k = 0; k < 9; ++k) {
+                const char *p1 = in_g + rb[k].x, *p3 = p1 + WCb;
+                const float4 w = rw[k];
+                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1 + Cb), v2);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3 + Cb), v4);
+                accumulate(w, v1, v2, v3, v4);
+            }
         } else {
-            for (int k = 0; k < P; ++k) sample(k);
+            for (int k = 0; k < P; ++k) {
+                const int2 bf = rb[k];
+                if (bf.y == 0) continue;   // sample out of range: contributes nothing (cuh:268-269)
+                const float4 w = rw[k];
+                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+                gather4<T, VEC>(in_g + bf.x, Cb, WCb, (unsigned)bf.y, v1, v2, v3, v4);
+                accumulate(w, v1, v2, v3, v4);
+            }
         }
-        const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
+        const long long q = ((long long)t.b * p.Ho + u.oh) * p.Wo + u.ow;
         Vec<T, VEC>::store_stream(out + q * C + g * p.gc + cl * VEC, acc);
     }
 }
@@ -298,7 +345,7 @@ __device__ __forceinline__ void unit_reduce3(float &a, float &b, float &c, int c
 }
 
 template <typename T, int VEC, int L, bool P9>
-__global__ void __launch_bounds__(kTileThreads)
+__global__ void __launch_bounds__(kTileThreads, kTileMinBlocks)
 dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ msk,
                const T *__restrict__ gout, float *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmsk,
                const __grid_constant__ KParams p) {
@@ -308,7 +355,8 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     const int n_rec = t.n_ul * P;
     float4 *s_w = smem4;
     int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
-    build_records<T, false, true>(off, msk, s_w, s_bf, nullptr, p, t);
+    unsigned *s_unit = reinterpret_cast<unsigned *>(s_bf + n_rec);
+    build_records<T, false, true, P9>(off, msk, s_w, s_bf, s_unit, nullptr, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;
@@ -319,15 +367,15 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     float *gin_b = gin + img + cl * VEC;
     constexpr int UPB = kTileThreads / L;
     const int n_pass = (t.n_ul + UPB - 1) / UPB;
+    const unsigned full = 0xffffffffu;
 
     for (int pass = 0; pass < n_pass; ++pass) {
         const int ul = pass * UPB + threadIdx.x / L;
-        const int gl = ul / t.TP, pix = ul - gl * t.TP;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
-        const bool valid = ul < t.n_ul && oh < p.Ho && ow < p.Wo;
-        if (!__any_sync(0xffffffffu, valid)) continue;   // warp-uniform
+        const UnitPos u = unit_pos(ul, p, t);
+        const bool valid = ul < t.n_ul && u.oh < p.Ho && u.ow < p.Wo;
+        if (!__any_sync(full, valid)) continue;   // warp-uniform
         const int ulc = valid ? ul : 0;
-        const int g = t.g0 + (valid ? gl : 0);
+        const int g = t.g0 + (valid ? u.gl : 0);
         const char *in_g = reinterpret_cast<const char *>(in_b + g * p.gc);
         char *gin_g = reinterpret_cast<char *>(gin_b + g * p.gc);
         float4 *rw = s_w + ulc * P;
@@ -337,79 +385,106 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
         for (int c = 0; c < VEC; ++c) go[c] = 0.f;
         if (valid) {
-            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
+            const long long q = ((long long)t.b * p.Ho + u.oh) * p.Wo + u.ow;
             Vec<T, VEC>::load_stream(gout + q * C + g * p.gc + cl * VEC, go);
         }
 
-        auto sample = [&](int k) {
-            const int2 bf = rb[k];
-            const unsigned flags = valid ? (unsigned)bf.y : 0u;
-            float s_m = 0.f, s_w_ = 0.f, s_h = 0.f;
-            if (flags) {
-                const float4 r = rw[k];
-                const float lh = r.x, lw = r.y, m = r.z;
-                const float hh = 1.f - lh, hw = 1.f - lw;
-                const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-                gather4<T, VEC>(in_g + bf.x, Cb, WCb, flags, v1, v2, v3, v4);
-                // d_k = sum_c top_grad[c] * v_k[c]: everything grad_offset / grad_mask need (cuh:107-146 are linear in v_k)
-                float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
+        // everything grad_offset / grad_mask need are the four dot products d_k = sum_c top_grad[c] * corner_k[c]
+        // (cuh:107-146 are linear in the corner values); s_m / s_w / s_h are this lane's partial sums
+        auto point_math = [&](const float4 r, const float (&v1)[VEC], const float (&v2)[VEC], const float (&v3)[VEC],
+                              const float (&v4)[VEC], float &s_m, float &s_w_, float &s_h, float (&mw)[4]) {
+            const float lh = r.x, lw = r.y, m = r.z;
+            const float hh = 1.f - lh, hw = 1.f - lw;
+            const float w1 = hh * hw, w2 = hh * lw, w3 = lh * hw, w4 = lh * lw;
+            float d1 = 0.f, d2 = 0.f, d3 = 0.f, d4 = 0.f;
 #pragma unroll
-                for (int c = 0; c < VEC; ++c) {
-                    d1 = fmaf(go[c], v1[c], d1);
-                    d2 = fmaf(go[c], v2[c], d2);
-                    d3 = fmaf(go[c], v3[c], d3);
-                    d4 = fmaf(go[c], v4[c], d4);
-                }
-                s_m = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;                  // cuh:144  sum_c top_grad * val
-                s_w_ = m * (hh * (d2 - d1) + lh * (d4 - d3));                 // cuh:145  grad_w_weight * top_grad * mask
-                s_h = m * (hw * (d3 - d1) + lw * (d4 - d2));                  // cuh:146  grad_h_weight * top_grad * mask
-                // cuh:116-140: grad_im[corner] += w_corner * top_grad * mask, one 16-byte reduction per corner
-                const float m1 = w1 * m, m2 = w2 * m, m3 = w3 * m, m4 = w4 * m;
-                char *g1 = gin_g + bf.x * GS, *g3 = g1 + WCb * GS;
-#pragma unroll
-                for (int c4 = 0; c4 < VEC; c4 += 4) {
-                    if (flags & F_C1) red_add_v4(reinterpret_cast<float *>(g1) + c4, m1 * go[c4], m1 * go[c4 + 1], m1 * go[c4 + 2], m1 * go[c4 + 3]);
-                    if (flags & F_C2) red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, m2 * go[c4], m2 * go[c4 + 1], m2 * go[c4 + 2], m2 * go[c4 + 3]);
-                    if (flags & F_C3) red_add_v4(reinterpret_cast<float *>(g3) + c4, m3 * go[c4], m3 * go[c4 + 1], m3 * go[c4 + 2], m3 * go[c4 + 3]);
-                    if (flags & F_C4) red_add_v4(reinterpret_cast<float *>(g3 + Cb * GS) + c4, m4 * go[c4], m4 * go[c4 + 1], m4 * go[c4 + 2], m4 * go[c4 + 3]);
-                }
+            for (int c = 0; c < VEC; ++c) {
+                d1 = fmaf(go[c], v1[c], d1);
+                d2 = fmaf(go[c], v2[c], d2);
+                d3 = fmaf(go[c], v3[c], d3);
+                d4 = fmaf(go[c], v4[c], d4);
             }
-            // sum over the gc channels of the group = reduction over the L lanes of this unit (no block barriers)
-            unit_reduce3<L>(s_m, s_w_, s_h, cl);
-            if (valid) {   // park the results in the (now consumed) record
-                float *slot = reinterpret_cast<float *>(rw + k);
-                if (L == 1) {
-                    slot[0] = p.scale * s_w_; slot[1] = p.scale * s_h; slot[2] = s_m;
-                } else if (L == 2) {
-                    if (cl == 0) { slot[2] = s_m; slot[0] = p.scale * s_w_; } else { slot[1] = p.scale * s_h; }
-                } else {
-                    if (cl == 0) slot[2] = s_m;
-                    else if (cl == 2) slot[0] = p.scale * s_w_;
-                    else if (cl == 1) slot[1] = p.scale * s_h;
-                }
+            s_m = w1 * d1 + w2 * d2 + w3 * d3 + w4 * d4;      // cuh:144  sum_c top_grad * val
+            s_w_ = m * (hh * (d2 - d1) + lh * (d4 - d3));     // cuh:145  grad_w_weight * top_grad * mask
+            s_h = m * (hw * (d3 - d1) + lw * (d4 - d2));      // cuh:146  grad_h_weight * top_grad * mask
+            mw[0] = w1 * m; mw[1] = w2 * m; mw[2] = w3 * m; mw[3] = w4 * m;   // cuh:116-140 corner weights * mask
+        };
+        // park the unit's three sums in the (consumed) record: lane 0 grad_mask, lane 2 (or 0) grad_off_w, lane 1 grad_off_h
+        auto park = [&](int k, float s_m, float s_w_, float s_h) {
+            float *slot = reinterpret_cast<float *>(rw + k);
+            if (L == 1) {
+                slot[0] = p.scale * s_w_; slot[1] = p.scale * s_h; slot[2] = s_m;
+            } else if (L == 2) {
+                if (cl == 0) { slot[2] = s_m; slot[0] = p.scale * s_w_; } else { slot[1] = p.scale * s_h; }
+            } else {
+                if (cl == 0) slot[2] = s_m;
+                else if (cl == 2) slot[0] = p.scale * s_w_;
+                else if (cl == 1) slot[1] = p.scale * s_h;
             }
         };
-        if (P9) {
+
+        if (P9 && __all_sync(full, valid && s_unit[ulc])) {
+            // every unit of the warp is interior: 36 unconditional gathers + 36 unconditional reductions, no branches
 #pragma unroll
-            for (int k = 0; k < 9; ++k) sample(k);
+            for (int k = 0; k < 9; ++k) {
+                const int base = rb[k].x;
+                const float4 r = rw[k];
+                const char *p1 = in_g + base, *p3 = p1 + WCb;
+                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1 + Cb), v2);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
+                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3 + Cb), v4);
+                float s_m, s_w_, s_h, mw[4];
+                point_math(r, v1, v2, v3, v4, s_m, s_w_, s_h, mw);
+                char *g1 = gin_g + base * GS, *g3 = g1 + WCb * GS;
+#pragma unroll
+                for (int c4 = 0; c4 < VEC; c4 += 4) {
+                    red_add_v4(reinterpret_cast<float *>(g1) + c4, mw[0] * go[c4], mw[0] * go[c4 + 1], mw[0] * go[c4 + 2], mw[0] * go[c4 + 3]);
+                    red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, mw[1] * go[c4], mw[1] * go[c4 + 1], mw[1] * go[c4 + 2], mw[1] * go[c4 + 3]);
+                    red_add_v4(reinterpret_cast<float *>(g3) + c4, mw[2] * go[c4], mw[2] * go[c4 + 1], mw[2] * go[c4 + 2], mw[2] * go[c4 + 3]);
+                    red_add_v4(reinterpret_cast<float *>(g3 + Cb * GS) + c4, mw[3] * go[c4], mw[3] * go[c4 + 1], mw[3] * go[c4 + 2], mw[3] * go[c4 + 3]);
+                }
+                unit_reduce3<L>(s_m, s_w_, s_h, cl);
+                park(k, s_m, s_w_, s_h);
+            }
         } else {
-            for (int k = 0; k < P; ++k) sample(k);
+            for (int k = 0; k < P; ++k) {
+                const int2 bf = rb[k];
+                const unsigned flags = valid ? (unsigned)bf.y : 0u;
+                float s_m = 0.f, s_w_ = 0.f, s_h = 0.f;
+                if (flags) {
+                    const float4 r = rw[k];
+                    float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+                    gather4<T, VEC>(in_g + bf.x, Cb, WCb, flags, v1, v2, v3, v4);
+                    float mw[4];
+                    point_math(r, v1, v2, v3, v4, s_m, s_w_, s_h, mw);
+                    char *g1 = gin_g + bf.x * GS, *g3 = g1 + WCb * GS;
+#pragma unroll
+                    for (int c4 = 0; c4 < VEC; c4 += 4) {
+                        if (flags & F_C1) red_add_v4(reinterpret_cast<float *>(g1) + c4, mw[0] * go[c4], mw[0] * go[c4 + 1], mw[0] * go[c4 + 2], mw[0] * go[c4 + 3]);
+                        if (flags & F_C2) red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, mw[1] * go[c4], mw[1] * go[c4 + 1], mw[1] * go[c4 + 2], mw[1] * go[c4 + 3]);
+                        if (flags & F_C3) red_add_v4(reinterpret_cast<float *>(g3) + c4, mw[2] * go[c4], mw[2] * go[c4 + 1], mw[2] * go[c4 + 2], mw[2] * go[c4 + 3]);
+                        if (flags & F_C4) red_add_v4(reinterpret_cast<float *>(g3 + Cb * GS) + c4, mw[3] * go[c4], mw[3] * go[c4 + 1], mw[3] * go[c4 + 2], mw[3] * go[c4 + 3]);
+                    }
+                }
+                // sum over the gc channels of the group = reduction over the L lanes of this unit (no block barriers)
+                unit_reduce3<L>(s_m, s_w_, s_h, cl);
+                if (valid) park(k, s_m, s_w_, s_h);
+            }
         }
     }
     __syncthreads();
 
     // coalesced write-back of grad_offset / grad_mask in global-memory order (inverse of the record permutation)
-    const int rowP = p.gs * P;
-    for (int e = threadIdx.x; e < t.TP * rowP; e += blockDim.x) {
-        const int pix = e / rowP, r = e - pix * rowP;
-        const int gl = r / P, pt = r - gl * P;
-        const int oh = t.oh0 + pix / p.tile_w, ow = t.ow0 + pix % p.tile_w;
+    for (int e = threadIdx.x; e < n_rec; e += blockDim.x) {
+        const int pg = e / P, pt = e - pg * P;
+        const int pix = pg >> p.lg_gs, gl = pg & (p.gs - 1);
+        const int oh = t.oh0 + (pix >> p.lg_tw), ow = t.ow0 + (pix & (p.tile_w - 1));
         if (oh < p.Ho && ow < p.Wo) {
             const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            const long long k = (q * p.G + t.g0) * (long long)P + r;
-            const int rec = (gl * t.TP + pix) * P + pt;
-            const float4 res = s_w[rec];   // out-of-range samples parked 0, 0, 0 (cuh:347-355)
+            const long long k = ((q * p.G + t.g0 + gl) * (long long)P) + pt;
+            const float4 res = s_w[(gl * t.TP + pix) * P + pt];   // out-of-range samples parked 0, 0, 0 (cuh:347-355)
             store_pair<T>(goff + 2 * k, res.x, res.y);
             gmsk[k] = from_acc<T, float>(res.z);
         }

@@ -28,7 +28,8 @@ struct KParams {
     int half_h, half_w;      // (dil*(k-1))>>1
     float scale;
     // tiling of the output plane used by the tiled kernels
-    int tile_h, tile_w, tiles_y, tiles_x, gs /*groups per CTA*/, gchunks /*G/gs*/;
+    int tile_h, tile_w, tiles_y, tiles_x, gs /*groups per CTA*/, gchunks /*G/gs*/;   // tile_h, tile_w, gs: powers of two
+    int lg_tw, lg_tp, lg_gs; // log2(tile_w), log2(tile_h*tile_w), log2(gs)
     long long n_units;       // N*Ho*Wo*G
 };
 

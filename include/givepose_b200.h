@@ -118,7 +118,8 @@ int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void
 int gp_host_cache_release(void);
 
 /* Tiling of the sampling kernels: output-tile height/width, groups per CTA and channels per lane for
- * 16-bit storage (4 or 8); values <= 0 keep the current setting; defaults 8, 8, 1, 8; also read once from
+ * 16-bit storage in the forward kernel (4 or 8); values <= 0 keep the current setting; tile sizes are rounded
+ * down to powers of two; defaults 8, 8, 2, 8; also read once from
  * GP_TILE_H / GP_TILE_W / GP_GS / GP_VEC16.  Used by the tuning sweeps in tools/; results never depend on it
  * beyond floating-point summation order. */
 int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);

@@ -11,9 +11,7 @@ echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 
 echo "== bench reference"; timeout 600 python bench.py --impl reference --steps 3 --warmup 1 2>&1 | tail -1
 echo "== bench f32"; timeout 600 python bench.py 2>&1 | tail -1
 echo "== bench bf16"; timeout 600 python bench.py --dtype bf16 --no-cpu-baseline 2>&1 | tail -1
-echo "== sweep"; timeout 900 python tools/sweep_dcnv3.py --out gpurun_out/sweep_${TAG}.json 2>&1 | tail -100
-echo "== sweep debug=1 (no grad_input reductions; WRONG results, timing only)"; GP_DEBUG=1 timeout 600 python tools/sweep_dcnv3.py --quick --out gpurun_out/sweep_${TAG}_dbg1.json 2>&1 | tail -30
-echo "== sweep debug=3 (no reductions, no lane shuffles)"; GP_DEBUG=3 timeout 600 python tools/sweep_dcnv3.py --quick --out gpurun_out/sweep_${TAG}_dbg3.json 2>&1 | tail -30
+echo "== bench f32 dist M"; timeout 600 python bench.py --dist M --no-cpu-baseline --no-e2e 2>&1 | tail -1
 } > gpurun_out/${TAG}_log.txt 2>&1
 # ncu: launch list of the bench command, then one full capture of the two sampling kernels
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
