@@ -39,6 +39,11 @@ EXPORTS = {
     "gp_dcnv3_forward_host": (_I, [_VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
     "gp_dcnv3_backward_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
     "gp_host_cache_release": (_I, []),
+    "gp_dwconv3x3_ln_gelu": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _I, _VP]),
+    "gp_groupnorm_act": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _VP]),
+    "gp_upsample_bilinear2x": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
+    "gp_maxpool3x3s2": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
+    "gp_pose_decode": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, ctypes.c_float, _VP]),
     "gp_set_tuning": (_I, [_I, _I, _I, _I]),
     "gp_launch_count": (ctypes.c_uint64, []),
     "gp_launch_count_reset": (None, []),

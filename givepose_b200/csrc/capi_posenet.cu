@@ -1,0 +1,117 @@
+// givepose_b200 -- C-ABI entry points of the PoseNet glue kernels (include/givepose_b200.h, "PoseNet forward" block).
+#include "posenet_kernels.cuh"
+
+using namespace gp;
+
+static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+extern "C" {
+
+int gp_dwconv3x3_ln_gelu(const void *x, const float *w_t, const float *bias, const float *ln_w, const float *ln_b, void *out,
+                         int N, int H, int W, int C, long long rows, float eps, int dtype, void *stream) {
+    if (!x || !w_t || !bias || !ln_w || !ln_b || !out) return GP_ERR_NULL;
+    if (N <= 0 || H <= 0 || W <= 0 || rows < 0 || rows > (long long)N * H * W) return GP_ERR_SHAPE;
+    if (C != 128 && C != 256 && C != 512) return GP_ERR_UNSUPPORTED;
+    if (!al16(x) || !al16(w_t) || !al16(bias) || !al16(ln_w) || !al16(ln_b) || !al16(out)) return GP_ERR_ALIGN;
+    if (rows == 0) return GP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long want = (rows + 7) / 8;   // 8 warps (pixels) per CTA
+    const unsigned grid = (unsigned)(want < 148ll * 64 ? want : 148ll * 64);
+#define GP_DW(TT, JJ) dwconv3x3_ln_gelu_kernel<TT, JJ><<<grid, 256, 0, st>>>((const TT *)x, w_t, bias, ln_w, ln_b, (TT *)out, H, W, rows, eps)
+#define GP_DW_T(TT) do { if (C == 128) GP_DW(TT, 1); else if (C == 256) GP_DW(TT, 2); else GP_DW(TT, 4); } while (0)
+    switch (dtype) {
+        case GP_F32: GP_DW_T(float); break;
+        case GP_BF16: GP_DW_T(__nv_bfloat16); break;
+        case GP_F16: GP_DW_T(__half); break;
+        default: return GP_ERR_DTYPE;
+    }
+#undef GP_DW_T
+#undef GP_DW
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+// slab decomposition shared by the channel-last elementwise kernels: grid (slabs, N), >= 32 pixels per CTA
+static dim3 slab_grid(int N, int npix, int ctas_per_sm, int *ppc) {
+    int slabs = (int)((148ll * ctas_per_sm + N - 1) / N);
+    if (slabs > (npix + 31) / 32) slabs = (npix + 31) / 32;
+    if (slabs < 1) slabs = 1;
+    *ppc = (npix + slabs - 1) / slabs;
+    return dim3((npix + *ppc - 1) / *ppc, N);
+}
+
+int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, const float *beta, int N, int H, int W, int C,
+                     int G, float eps, int act, int dtype, void *stream) {
+    if (!x || !y || !stats || !gamma || !beta) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || C % G || (C / G) % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (act < 0 || act > 2) return GP_ERR_UNSUPPORTED;
+    if (!al16(x) || !al16(y) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(stats, 0, (size_t)N * G * 2 * sizeof(float), st);
+    if (ce != cudaSuccess) return (int)ce;
+    const int HW = H * W;
+    int ppc = 0, appc = 0;
+    const dim3 sgrid = slab_grid(N, HW, 8, &ppc), agrid = slab_grid(N, HW, 16, &appc);
+#define GP_GN_APPLY(TT, AA) gn_apply_kernel<TT, AA><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, (TT *)y, HW, C, G, eps, appc)
+#define GP_GN(TT) do { gn_stats_kernel<TT><<<sgrid, 256, 2 * G * sizeof(float), st>>>((const TT *)x, stats, HW, C, G, ppc); \
+                       if (act == ACT_RELU) GP_GN_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GN_APPLY(TT, ACT_GELU); \
+                       else GP_GN_APPLY(TT, ACT_NONE); } while (0)
+    switch (dtype) {
+        case GP_F32: GP_GN(float); break;
+        case GP_BF16: GP_GN(__nv_bfloat16); break;
+        case GP_F16: GP_GN(__half); break;
+        default: return GP_ERR_DTYPE;
+    }
+#undef GP_GN
+#undef GP_GN_APPLY
+    count_launch(2);
+    return (int)cudaGetLastError();
+}
+
+int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream) {
+    if (!x || !y) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || C % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (!al16(x) || !al16(y)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int ppc = 0;
+    const dim3 grid = slab_grid(N, 4 * H * W, 16, &ppc);
+    switch (dtype) {
+        case GP_F32: upsample2x_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, H, W, C, ppc); break;
+        case GP_BF16: upsample2x_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, H, W, C, ppc); break;
+        case GP_F16: upsample2x_kernel<__half><<<grid, 256, 0, st>>>((const __half *)x, (__half *)y, H, W, C, ppc); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream) {
+    if (!x || !y) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || C % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (!al16(x) || !al16(y)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+    int ppc = 0;
+    const dim3 grid = slab_grid(N, Ho * Wo, 16, &ppc);
+    switch (dtype) {
+        case GP_F32: maxpool3x3s2_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
+        case GP_BF16: maxpool3x3s2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
+        case GP_F16: maxpool3x3s2_kernel<__half><<<grid, 256, 0, st>>>((const __half *)x, (__half *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_pose_decode(const float *rot6, const float *t, const float *cam, int cam_batched, const float *centers, const float *whs,
+                   const float *ratios, float *rot_out, float *trans_out, int B, int is_allo, float z_calib, void *stream) {
+    if (!rot6 || !t || !cam || !centers || !whs || !ratios || !rot_out || !trans_out) return GP_ERR_NULL;
+    if (B < 0) return GP_ERR_SHAPE;
+    if (B == 0) return GP_OK;
+    pose_decode_kernel<<<(B + 127) / 128, 128, 0, (cudaStream_t)stream>>>(rot6, t, cam, cam_batched ? 9 : 0, centers, whs, ratios,
+                                                                         rot_out, trans_out, B, is_allo, z_calib);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

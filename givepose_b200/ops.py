@@ -1,0 +1,116 @@
+"""Host wrappers of the fused PoseNet glue kernels (``include/givepose_b200.h``, "PoseNet forward" block).
+
+Each wrapper validates like the DCNv3 boundary does (CUDA, contiguous, supported dtype), allocates its output on the
+input's device and enqueues on the current torch stream.  No CPU / PyTorch fallback: a CPU tensor raises.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_DTYPES = {torch.float32: _lib.GP_F32, torch.bfloat16: _lib.GP_BF16, torch.float16: _lib.GP_F16}
+ACT = {"none": 0, "relu": 1, "gelu": 2}
+
+
+def _vp(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream(t):
+    return ctypes.c_void_p(torch.cuda.current_stream(t.device).cuda_stream)
+
+
+def _need_cuda(name, t, dtype=None):
+    if not t.is_cuda:
+        raise RuntimeError(f"{name}: Not implemented on the CPU")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} tensor has to be contiguous")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+
+
+def dwconv3x3_ln_gelu(x, w_t, bias, ln_w, ln_b, rows=None, eps=1e-6):
+    """``GELU(LayerNorm(DWConv3x3(x)))`` of the DCNv3 module (``modules/dcnv3.py:269-283,329``) for the first ``rows``
+    pixels of channel-last ``x`` (N,H,W,C); returns ``(rows, C)``.  ``w_t`` is the depthwise weight as ``[9, C]`` fp32."""
+    _need_cuda("input", x)
+    for n, t in (("dw weight", w_t), ("dw bias", bias), ("ln weight", ln_w), ("ln bias", ln_b)):
+        _need_cuda(n, t, torch.float32)
+    dt = _DTYPES.get(x.dtype)
+    if dt is None or x.dim() != 4:
+        raise RuntimeError(f"dwconv3x3_ln_gelu: unsupported input {x.dtype} {tuple(x.shape)}")
+    N, H, W, C = x.shape
+    rows = N * H * W if rows is None else int(rows)
+    out = torch.empty((rows, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_dwconv3x3_ln_gelu(_vp(x), _vp(w_t), _vp(bias), _vp(ln_w), _vp(ln_b), _vp(out), N, H, W, C, rows,
+                                       float(eps), dt, _stream(x)), "dwconv3x3_ln_gelu")
+    return out
+
+
+def _nhwc(name, x):
+    _need_cuda(name, x)
+    dt = _DTYPES.get(x.dtype)
+    if dt is None or x.dim() != 4:
+        raise RuntimeError(f"{name}: unsupported input {x.dtype} {tuple(x.shape)}")
+    return dt
+
+
+def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=False):
+    """``act(GroupNorm(x))`` on channel-last ``x`` (N,H,W,C); ``upsample2x`` appends the align_corners=True bilinear x2
+    upsampling of ``TopDownXyzHead`` (a second pass: see posenet_kernels.cuh).  ``gamma`` / ``beta`` are fp32."""
+    dt = _nhwc("input", x)
+    _need_cuda("gn weight", gamma, torch.float32)
+    _need_cuda("gn bias", beta, torch.float32)
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_groupnorm_act(_vp(x), _vp(y), _vp(stats), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
+                                   ACT[act], dt, _stream(x)), "groupnorm_act")
+    return upsample_bilinear2x(y) if upsample2x else y
+
+
+def upsample_bilinear2x(x):
+    """``nn.UpsamplingBilinear2d(scale_factor=2)`` (align_corners=True) on channel-last ``x``."""
+    dt = _nhwc("input", x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, 2 * H, 2 * W, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_upsample_bilinear2x(_vp(x), _vp(y), N, H, W, C, dt, _stream(x)), "upsample_bilinear2x")
+    return y
+
+
+def maxpool3x3s2(x, relu=False):
+    """``MaxPool2d(3, 2, 1)`` on channel-last ``x`` (N,H,W,C); ``relu=True`` computes ``maxpool(relu(x))`` in the same pass."""
+    dt = _nhwc("input", x)
+    N, H, W, C = x.shape
+    y = torch.empty((N, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_maxpool3x3s2(_vp(x), _vp(y), N, H, W, C, int(bool(relu)), dt, _stream(x)), "maxpool3x3s2")
+    return y
+
+
+def pose_decode(rot6, t, cam_K, centers, whs, ratios, is_allo=True, z_calib=1.0):
+    """rot6d -> R, back-projection and allo->ego on the device (replaces the host loop of
+    ``pose_from_predictions_test``, ``pose_from_pred_centroid_z.py:139-157``).  Returns ``(rot (B,3,3), trans (B,3))``."""
+    args = [("rot6", rot6), ("t", t), ("cam_K", cam_K), ("bbox_center", centers), ("roi_wh", whs), ("resize_ratio", ratios)]
+    args = [(n, a.float().contiguous()) for n, a in args]
+    for n, a in args:
+        _need_cuda(n, a, torch.float32)
+    rot6, t, cam_K, centers, whs, ratios = (a for _, a in args)
+    B = rot6.shape[0]
+    if rot6.shape != (B, 6) or t.shape != (B, 3) or centers.shape != (B, 2) or whs.shape != (B, 2) or ratios.numel() != B:
+        raise RuntimeError("pose_decode: inconsistent shapes")
+    if cam_K.numel() not in (9, 9 * B):
+        raise RuntimeError("pose_decode: cam_K must be (3,3), (1,3,3) or (B,3,3)")
+    batched = cam_K.dim() == 3 and cam_K.shape[0] == B   # (1,3,3) with B == 1 reads the same 9 floats either way
+    rot = torch.empty((B, 3, 3), dtype=torch.float32, device=rot6.device)
+    trans = torch.empty((B, 3), dtype=torch.float32, device=rot6.device)
+    with torch.cuda.device(rot6.device):
+        check(lib.gp_pose_decode(_vp(rot6), _vp(t), _vp(cam_K), int(batched), _vp(centers), _vp(whs), _vp(ratios),
+                                 _vp(rot), _vp(trans), B, int(bool(is_allo)), float(z_calib), _stream(rot6)), "pose_decode")
+    return rot, trans

@@ -1,0 +1,578 @@
+"""Per-RoI ``PoseNet`` inference forward on B200: host-side mirror of the reference model surface.
+
+Mirrors (reference file:line, relative to /root/reference):
+
+* ``PoseNet.__init__/forward(data, device, do_loss=False, pred_scale=None)``   network/PoseNet.py:134-231
+* ``DCNv3`` / ``DCNv3_C``                     network/ops_dcnv3/modules/dcnv3.py:221-356, network/dcnv3.py:23-38
+* ``MAPEncoder`` / ``ConvPnPNet``             network/conv_pnp_net.py:203-332 / :18-201
+* ``TopDownXyzHead`` / ``ConvModule``         network/xyz_head.py:195-366, torch_utils/layers/conv_module.py:57-234
+* ``SizeHead``                                network/pose_head.py:17-51
+* pose decode                                 network/pose_utils/{rot_reps.py:34-55, pose_from_pred_centroid_z.py:59-157,
+                                              utils.py:29-84}
+
+Same module tree and state-dict keys (a reference checkpoint of the heads loads with ``strict=True``), same input dict,
+same output dict -- ``rot`` comes back on the CPU like the reference's test path (``pose_from_pred_centroid_z.py:157``)
+unless ``cfg.rot_on_cpu`` is cleared.
+
+What runs where (inference, ``torch.no_grad``):
+
+* DCNv3 core, its ``dw_conv -> LayerNorm -> GELU`` prologue, every ``GroupNorm -> ReLU/GELU`` (+ the bilinear x2
+  upsampling that follows it in the decoder) and the whole pose decode are hand-written sm_100a kernels behind the C ABI
+  (``givepose_b200/ops.py``, ``functions.py``); activations stay channel-last end to end, so the reference's
+  NCHW<->NHWC permutes (``network/dcnv3.py:33-36``) disappear.
+* The mask softmax is fused into the sampler (``mask_is_logits``), and ``dw_conv/LN/GELU/offset/mask`` are evaluated only
+  for the ``N*Ho*Wo`` pixel rows the sampler actually reads: 4x less work at stride 2, same result.
+* Dense projections / convolutions (1x1, Linear, 3x3, deconv, backbone) are library GEMMs/convs (cuBLAS / cuDNN through
+  torch) -- fp32 with TF32 disabled in ``precision='fp32'`` (the 1e-4 parity mode), bf16 tensor cores in ``'bf16'``.
+* With autograd enabled (training step) the glue falls back to differentiable torch CUDA ops around ``DCNv3Function``
+  (custom backward kernel); there is no CPU path in either mode.
+"""
+from __future__ import annotations
+
+import contextlib
+from dataclasses import dataclass
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import ops
+from .functions import DCNv3Function, dcnv3_forward
+
+
+@dataclass
+class PoseNetConfig:
+    """The absl FLAGS the reference reads at construction / call time (config/config.py defaults)."""
+    img_size: int = 256
+    out_res: int = 64
+    feat_ts: int = 128            # SizeHead hidden width (FLAGS.feat_ts)
+    size_head_out_dim: int = 3
+    r_type: str = "allo_rot6d"
+    t_type: str = "site"
+    dataset: str = "Real"         # 'wild6d' rescales z by fx/590 (pose_from_pred_centroid_z.py:110-111)
+    precision: str = "fp32"       # 'fp32' (TF32 off, parity mode) | 'bf16'
+    rot_on_cpu: bool = True       # reference behaviour at test time
+
+
+def _fused(x: torch.Tensor) -> bool:
+    return not torch.is_grad_enabled()
+
+
+def _cached(p: torch.Tensor, dtype, fn=None, tag=""):
+    """Derived inference copy of a parameter (dtype cast, channels_last layout, reshapes ...), rebuilt when the parameter
+    changes (in-place updates bump ``_version``).  Keeps the fp32 master weights / state-dict untouched in bf16 mode and
+    avoids re-casting every weight on every forward (what autocast would do)."""
+    cache = getattr(p, "_gp_cache", None)
+    if cache is None:
+        cache = {}
+        p._gp_cache = cache
+    key = (dtype, tag)
+    hit = cache.get(key)
+    if hit is None or hit[0] != p._version or hit[1].device != p.device:
+        with torch.no_grad():
+            t = p.detach()
+            t = (fn(t) if fn is not None else t).to(dtype)
+            t = t.contiguous(memory_format=torch.channels_last) if t.dim() == 4 else t.contiguous()
+        cache[key] = (p._version, t)
+        return t
+    return hit[1]
+
+
+def _lin(x, lin: nn.Linear):
+    """Linear on channel-last rows; inference uses the cached weight copy in the activation dtype."""
+    if not _fused(x):
+        return lin(x)
+    return F.linear(x, _cached(lin.weight, x.dtype), _cached(lin.bias, x.dtype))
+
+
+def _conv1x1_rows(x, conv: nn.Conv2d):
+    """A 1x1 convolution is a Linear over the channel-last rows."""
+    if not _fused(x):
+        return F.linear(x, conv.weight.flatten(1), conv.bias)
+    return F.linear(x, _cached(conv.weight, x.dtype, lambda w: w.flatten(1), "rows"),
+                    None if conv.bias is None else _cached(conv.bias, x.dtype))
+
+
+# ----------------------------------------------------------------------------------------------------------
+# DCNv3 module + NCHW wrapper
+# ----------------------------------------------------------------------------------------------------------
+class _ToChannelsLast(nn.Module):
+    def forward(self, x):
+        return x.permute(0, 2, 3, 1)
+
+
+class DCNv3(nn.Module):
+    """Drop-in for ``ops_dcnv3.modules.dcnv3.DCNv3``: channel-last ``(N,H,W,C) -> (N,Ho,Wo,C)``."""
+
+    def __init__(self, channels=64, kernel_size=3, dw_kernel_size=None, stride=1, pad=1, dilation=1, group=4,
+                 offset_scale=1.0, act_layer="GELU", norm_layer="LN", center_feature_scale=False, remove_center=False):
+        super().__init__()
+        if channels % group != 0:
+            raise ValueError(f"channels must be divisible by group, but got {channels} and {group}")
+        if act_layer != "GELU" or norm_layer != "LN" or center_feature_scale:
+            raise NotImplementedError("GIVEPose builds DCNv3 with GELU / LN / center_feature_scale=False (network/dcnv3.py:26-28)")
+        dw_kernel_size = kernel_size if dw_kernel_size is None else dw_kernel_size
+        self.channels, self.kernel_size, self.dw_kernel_size = channels, kernel_size, dw_kernel_size
+        self.stride, self.pad, self.dilation, self.group = stride, pad, dilation, group
+        self.group_channels, self.offset_scale = channels // group, offset_scale
+        self.center_feature_scale, self.remove_center = False, int(remove_center)
+        if self.remove_center and kernel_size % 2 == 0:
+            raise ValueError("remove_center is only compatible with odd kernel size.")
+        P = kernel_size * kernel_size - self.remove_center
+        self.dw_conv = nn.Sequential(
+            nn.Conv2d(channels, channels, dw_kernel_size, 1, (dw_kernel_size - 1) // 2, groups=channels),
+            nn.Sequential(_ToChannelsLast(), nn.LayerNorm(channels, eps=1e-6)), nn.GELU())
+        self.offset = nn.Linear(channels, group * P * 2)
+        self.mask = nn.Linear(channels, group * P)
+        self.input_proj = nn.Linear(channels, channels)
+        self.output_proj = nn.Linear(channels, channels)
+        self._reset_parameters()
+        self._cache = {}
+
+    def _reset_parameters(self):   # modules/dcnv3.py:308-316
+        for m in (self.offset, self.mask):
+            nn.init.zeros_(m.weight)
+            nn.init.zeros_(m.bias)
+        for m in (self.input_proj, self.output_proj):
+            nn.init.xavier_uniform_(m.weight)
+            nn.init.zeros_(m.bias)
+
+    def _out_hw(self, H, W):
+        f = lambda n: (n + 2 * self.pad - (self.dilation * (self.kernel_size - 1) + 1)) // self.stride + 1
+        return f(H), f(W)
+
+    def _dw_params(self, device):
+        key = (device, self.dw_conv[0].weight._version, self.dw_conv[1][1].weight._version)
+        if self._cache.get("key") != key:
+            conv, ln = self.dw_conv[0], self.dw_conv[1][1]
+            self._cache = {"key": key,
+                           "w_t": conv.weight.detach().float().reshape(self.channels, -1).t().contiguous(),
+                           "b": conv.bias.detach().float().contiguous(),
+                           "ln_w": ln.weight.detach().float().contiguous(), "ln_b": ln.bias.detach().float().contiguous()}
+        return self._cache
+
+    def forward(self, input):
+        N, H, W, C = input.shape
+        k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
+        geom = (k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale)
+        x = _lin(input, self.input_proj)
+        fusable = (_fused(input) and self.dw_kernel_size == 3 and C in (128, 256, 512) and input.is_cuda
+                   and input.dtype in (torch.float32, torch.bfloat16, torch.float16))
+        if fusable:
+            # the sampler reads offset / mask through their flat [N*Ho*Wo]-row prefix (cuh:229,243-244): compute only those rows
+            Ho, Wo = self._out_hw(H, W)
+            rows = min(N * Ho * Wo, N * H * W)
+            c = self._dw_params(input.device)
+            x1 = ops.dwconv3x3_ln_gelu(input.contiguous(), c["w_t"], c["b"], c["ln_w"], c["ln_b"], rows, eps=1e-6)
+            offset = _lin(x1, self.offset)
+            logits = _lin(x1, self.mask)
+            x = dcnv3_forward(x.contiguous(), offset.contiguous(), logits.contiguous(), *geom, 256, self.remove_center,
+                              mask_is_logits=True)
+        else:
+            x1 = self.dw_conv(input.permute(0, 3, 1, 2))
+            offset = self.offset(x1)
+            mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(x.dtype)
+            x = DCNv3Function.apply(x.contiguous(), offset.contiguous(), mask.contiguous(), *geom, 256, self.remove_center)
+        return _lin(x, self.output_proj)
+
+
+class DCNv3_C(nn.Module):
+    """``network/dcnv3.py:23-38``: 1x1 conv -> DCNv3 (channel-last inside).  NCHW in / NCHW out like the reference;
+    ``forward_nhwc`` is the permute-free entry the fused encoder uses."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=1, stride=1, groups=4, dilation=1, padding=1, bias=False):
+        super().__init__()
+        self.conv = nn.Conv2d(in_channels, out_channels, kernel_size=1)
+        self.dcnv3 = DCNv3(out_channels, kernel_size=kernel_size, stride=stride, group=groups, dilation=dilation)
+        self.bn = nn.BatchNorm2d(out_channels)   # built but unused in the reference (:29,37); kept for checkpoint keys
+        self.gelu = nn.GELU()
+
+    def forward_nhwc(self, x):
+        return self.dcnv3(_conv1x1_rows(x, self.conv))
+
+    def forward(self, x):
+        return self.forward_nhwc(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+def _gn_act_nhwc(x, gn: nn.GroupNorm, act: str, upsample2x=False):
+    """GroupNorm -> act (-> bilinear x2) on channel-last activations: fused kernel at inference, torch ops under autograd."""
+    if _fused(x):
+        return ops.groupnorm_act(x.contiguous(), _cached(gn.weight, torch.float32), _cached(gn.bias, torch.float32),
+                                 gn.num_groups, gn.eps, act, upsample2x)
+    y = F.group_norm(x.permute(0, 3, 1, 2), gn.num_groups, gn.weight, gn.bias, gn.eps)
+    y = F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+    if upsample2x:
+        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+    return y.permute(0, 2, 3, 1)
+
+
+def _conv_nhwc(x, conv: nn.Module):
+    """cuDNN convolution on a channel-last activation without layout copies: (N,H,W,C) viewed as channels_last NCHW."""
+    xn = x.permute(0, 3, 1, 2)
+    if not _fused(x):
+        return conv(xn).permute(0, 2, 3, 1)
+    w = _cached(conv.weight, x.dtype)
+    b = None if conv.bias is None else _cached(conv.bias, x.dtype)
+    if isinstance(conv, nn.ConvTranspose2d):
+        y = F.conv_transpose2d(xn, w, b, conv.stride, conv.padding, conv.output_padding, conv.groups, conv.dilation)
+    else:
+        y = F.conv2d(xn, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    return y.permute(0, 2, 3, 1)
+
+
+class MAPEncoder(nn.Module):
+    """``conv_pnp_net.py:203-332`` with ``FLAGS.use_dcn == 'dcnv3'``: 3 x [DCNv3_C(stride 2) -> GN(32) -> ReLU]."""
+
+    def __init__(self, nIn, featdim=128, outdim=256, num_stride2_layers=3, num_gn_groups=32):
+        super().__init__()
+        self.features = nn.ModuleList()
+        for i in range(num_stride2_layers):
+            cin = nIn if i == 0 else featdim
+            featdim = outdim if i == num_stride2_layers - 1 else featdim
+            self.features += [DCNv3_C(cin, featdim, kernel_size=3, stride=2, padding=1, bias=False),
+                              nn.GroupNorm(num_gn_groups, featdim), nn.ReLU(inplace=True)]
+        for m in self.modules():   # :291-300
+            if isinstance(m, (nn.Conv2d, nn.Conv1d, nn.ConvTranspose2d, nn.Linear)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, (nn.GroupNorm, nn.BatchNorm2d)):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+
+    def forward_nhwc(self, x):
+        for i in range(0, len(self.features), 3):
+            x = _gn_act_nhwc(self.features[i].forward_nhwc(x), self.features[i + 1], "relu")
+        return x
+
+    def forward(self, coor_feat=None, mask_attention=None, cat_id=None, sp2d=None):
+        return self.forward_nhwc(coor_feat.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+# ----------------------------------------------------------------------------------------------------------
+# coordinate-map decoder
+# ----------------------------------------------------------------------------------------------------------
+class ConvModule(nn.Module):
+    def __init__(self, cin, cout, kernel_size=3, padding=1, num_gn_groups=32):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, kernel_size, padding=padding, bias=False)
+        self.norm = nn.GroupNorm(num_gn_groups, cout)
+        self.gn = self.norm   # the reference registers the same GroupNorm under both names (conv_module.py:181-183)
+        self.activate = nn.GELU()
+        nn.init.kaiming_normal_(self.conv.weight, a=0, mode="fan_out", nonlinearity="relu")
+
+    def forward_nhwc(self, x, upsample2x=False):
+        return _gn_act_nhwc(_conv_nhwc(x, self.conv), self.norm, "gelu", upsample2x)
+
+    def forward(self, x):
+        return self.forward_nhwc(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+class TopDownXyzHead(nn.Module):
+    """``xyz_head.py:195-366`` at its defaults: deconv -> GN -> GELU, 2 ConvModules, [bilinear x2, 2 ConvModules] x 2,
+    1x1 out layer -> (x, y, z) maps."""
+
+    def __init__(self, in_dim, feat_dim=256, num_gn_groups=32, xyz_num_classes=1):
+        super().__init__()
+        f = [nn.ConvTranspose2d(in_dim, feat_dim, 3, stride=2, padding=1, output_padding=1, bias=False),
+             nn.GroupNorm(num_gn_groups, feat_dim), nn.GELU(), ConvModule(feat_dim, feat_dim), ConvModule(feat_dim, feat_dim)]
+        for _ in range(2):
+            f += [nn.UpsamplingBilinear2d(scale_factor=2), ConvModule(feat_dim, feat_dim), ConvModule(feat_dim, feat_dim)]
+        self.features = nn.ModuleList(f)
+        self.out_layer = nn.Conv2d(feat_dim, 3 * xyz_num_classes, 1)
+        for m in self.modules():   # :334-347
+            if isinstance(m, (nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.normal_(m.weight, std=0.001)
+            elif isinstance(m, nn.GroupNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        nn.init.normal_(self.out_layer.weight, std=0.01)
+        nn.init.zeros_(self.out_layer.bias)
+
+    def forward_nhwc(self, x):
+        """x: (B, 8, 8, in_dim) channel-last -> (B, 64, 64, 3) channel-last."""
+        fs = self.features
+        x = _gn_act_nhwc(_conv_nhwc(x, fs[0]), fs[1], "gelu")
+        x = fs[3].forward_nhwc(x)
+        x = fs[4].forward_nhwc(x, upsample2x=True)     # features.5: bilinear x2 fused into the GN/GELU apply pass
+        x = fs[6].forward_nhwc(x)
+        x = fs[7].forward_nhwc(x, upsample2x=True)     # features.8
+        x = fs[9].forward_nhwc(x)
+        x = fs[10].forward_nhwc(x)
+        return _conv1x1_rows(x, self.out_layer)
+
+    def forward(self, x):
+        if isinstance(x, (tuple, list)) and len(x) == 1:
+            x = x[0]
+        out = self.forward_nhwc(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+        return out[:, 0:1], out[:, 1:2], out[:, 2:3]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# PnP regression head, size head
+# ----------------------------------------------------------------------------------------------------------
+class ConvPnPNet(nn.Module):
+    def __init__(self, nIn, featdim=128, rot_dim=6, num_gn_groups=32, mask_attention_type="none", flat_op="flatten"):
+        super().__init__()
+        if mask_attention_type != "none" or flat_op != "flatten":
+            raise NotImplementedError("GIVEPose runs ConvPnPNet with mask_attention_type='none', flat_op='flatten' (config.py)")
+        self.features = nn.ModuleList()
+        for i in range(3):
+            self.features += [nn.Conv2d(nIn if i == 0 else featdim, featdim, 3, 2, 1, bias=False),
+                              nn.GroupNorm(num_gn_groups, featdim), nn.ReLU(inplace=True)]
+        self.fc1, self.fc2 = nn.Linear(featdim * 64, 1024), nn.Linear(1024, 256)
+        self.fc1_z, self.fc2_z = nn.Linear(featdim * 64, 1024), nn.Linear(1024, 256)
+        self.fc_z, self.fc_r, self.fc_t = nn.Linear(256, 1), nn.Linear(256, rot_dim), nn.Linear(256, 2)
+        for m in self.modules():   # :124-134
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.normal_(m.weight, std=0.001)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.GroupNorm):
+                nn.init.ones_(m.weight)
+                nn.init.zeros_(m.bias)
+        nn.init.normal_(self.fc_r.weight, std=0.01)
+        nn.init.normal_(self.fc_t.weight, std=0.01)
+
+    def forward_nhwc(self, x):
+        for i in range(0, 9, 3):
+            x = _gn_act_nhwc(_conv_nhwc(x, self.features[i]), self.features[i + 1], "relu")
+        pnp_feat = x.permute(0, 3, 1, 2)
+        flat = pnp_feat.reshape(x.shape[0], -1)   # NCHW flatten order (conv_pnp_net.py:168-170): checkpoint compatible
+        # fc1 || fc1_z read the same 8192-wide activation: one GEMM over the concatenated weights
+        if _fused(x):
+            vers = (self.fc1.weight._version, self.fc1_z.weight._version, self.fc1.bias._version, self.fc1_z.bias._version, flat.dtype, flat.device)
+            if getattr(self, "_fc1_cat", (None,))[0] != vers:
+                self._fc1_cat = (vers, torch.cat([self.fc1.weight, self.fc1_z.weight]).detach().to(flat.dtype).contiguous(),
+                                 torch.cat([self.fc1.bias, self.fc1_z.bias]).detach().to(flat.dtype).contiguous())
+            h = F.leaky_relu(F.linear(flat, self._fc1_cat[1], self._fc1_cat[2]), 0.1)
+        else:
+            h = F.leaky_relu(F.linear(flat, torch.cat([self.fc1.weight, self.fc1_z.weight]), torch.cat([self.fc1.bias, self.fc1_z.bias])), 0.1)
+        hr = F.leaky_relu(_lin(h[:, :1024], self.fc2), 0.1)
+        hz = F.leaky_relu(_lin(h[:, 1024:], self.fc2_z), 0.1)
+        rot = _lin(hr, self.fc_r)
+        t = torch.cat([_lin(hr, self.fc_t), _lin(hz, self.fc_z)], dim=1)
+        return rot, t, pnp_feat
+
+    def forward(self, coor_feat=None, mask_attention=None, cat_id=None, sp2d=None):
+        return self.forward_nhwc(coor_feat.permute(0, 2, 3, 1))
+
+
+class SizeHead(nn.Module):
+    def __init__(self, in_dim, out_dim, feat_dim=128):
+        super().__init__()
+        self.conv1, self.conv2 = nn.Conv1d(in_dim, feat_dim, 1), nn.Conv1d(feat_dim, out_dim, 1)
+        self.drop1, self.bn1 = nn.Dropout(0.2), nn.BatchNorm1d(feat_dim)
+        for m in (self.conv1, self.conv2):
+            nn.init.normal_(m.weight, std=0.001)
+            nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        if isinstance(x, (tuple, list)) and len(x) == 1:
+            x = x[0]
+        x = x.flatten(2, 3).max(dim=-1, keepdim=True).values
+        if _fused(x) and not self.training:   # eval: BN = affine with running stats, Dropout = identity
+            bn = self.bn1
+            h = F.linear(x.squeeze(2).float(), self.conv1.weight.squeeze(2), self.conv1.bias)
+            h = F.relu((h - bn.running_mean) * torch.rsqrt(bn.running_var + bn.eps) * bn.weight + bn.bias)
+            return F.linear(h, self.conv2.weight.squeeze(2), self.conv2.bias)[:, :3]
+        x = self.conv2(self.drop1(F.relu(self.bn1(self.conv1(x)))))
+        return x.squeeze(2).contiguous()[:, :3]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# backbone of the synthetic runs: ResNet-34 trunk + 1x1 neck to the 1024 channels PoseNet hard-codes (PoseNet.py:144).
+# Plain torch modules (cuDNN); the reference uses timm's pretrained ConvNeXt-B here, which needs the network.
+# ----------------------------------------------------------------------------------------------------------
+class _Block(nn.Module):
+    def __init__(self, cin, cout, stride):
+        super().__init__()
+        self.conv1, self.bn1 = nn.Conv2d(cin, cout, 3, stride, 1, bias=False), nn.BatchNorm2d(cout)
+        self.conv2, self.bn2 = nn.Conv2d(cout, cout, 3, 1, 1, bias=False), nn.BatchNorm2d(cout)
+        self.downsample = None
+        if stride != 1 or cin != cout:
+            self.downsample = nn.Sequential(nn.Conv2d(cin, cout, 1, stride, bias=False), nn.BatchNorm2d(cout))
+
+    def forward(self, x):
+        idt = x if self.downsample is None else self.downsample(x)
+        return F.relu(self.bn2(self.conv2(F.relu(self.bn1(self.conv1(x))))) + idt)
+
+
+class ResNet34Trunk(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.conv1, self.bn1 = nn.Conv2d(3, 64, 7, 2, 3, bias=False), nn.BatchNorm2d(64)
+        cin = 64
+        for li, (c, n, s) in enumerate(((64, 3, 1), (128, 4, 2), (256, 6, 2), (512, 3, 2)), 1):
+            setattr(self, f"layer{li}", nn.Sequential(*[_Block(cin if b == 0 else c, c, s if b == 0 else 1) for b in range(n)]))
+            cin = c
+
+    def forward(self, x):
+        x = F.max_pool2d(F.relu(self.bn1(self.conv1(x))), 3, 2, 1)
+        return self.layer4(self.layer3(self.layer2(self.layer1(x))))
+
+
+def _folded(conv: nn.Conv2d, bn: nn.BatchNorm2d, dtype):
+    """eval-mode BatchNorm folded into the preceding convolution: w' = w * g/sqrt(var+eps), b' = beta - mean * g/sqrt(var+eps)."""
+    vers = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, dtype,
+            conv.weight.device)
+    hit = getattr(conv, "_gp_fold", None)
+    if hit is None or hit[0] != vers:
+        with torch.no_grad():
+            scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+            w = (conv.weight.float() * scale.view(-1, 1, 1, 1)).to(dtype).contiguous(memory_format=torch.channels_last)
+            b = (bn.bias.float() - bn.running_mean.float() * scale).to(dtype).contiguous()
+        hit = (vers, w, b)
+        conv._gp_fold = hit
+    return hit[1], hit[2]
+
+
+def _conv_bn_act(x, conv, bn, relu=True, residual=None):
+    """conv -> folded BN (-> + residual) (-> ReLU) with cuDNN's fused epilogue when this torch build exposes it."""
+    w, b = _folded(conv, bn, x.dtype)
+    if relu and hasattr(torch, "cudnn_convolution_relu") and _conv_bn_act.fused_ok:
+        try:
+            if residual is None:
+                return torch.cudnn_convolution_relu(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+            return torch.cudnn_convolution_add_relu(x, w, residual, 1.0, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+        except RuntimeError:
+            _conv_bn_act.fused_ok = False   # fall through to conv + elementwise (still cuDNN, still on the device)
+    y = F.conv2d(x, w, b, conv.stride, conv.padding, conv.dilation, conv.groups)
+    if residual is not None:
+        y = y.add_(residual)
+    return y.relu_() if relu else y
+
+
+_conv_bn_act.fused_ok = True
+
+
+def _stem(x, conv, bn):
+    """7x7/2 stem conv + folded BN, then ReLU + 3x3/2 max-pool in one channel-last kernel (ReLU commutes with max)."""
+    w, b = _folded(conv, bn, x.dtype)
+    y = F.conv2d(x, w, b, conv.stride, conv.padding)
+    y = ops.maxpool3x3s2(y.permute(0, 2, 3, 1).contiguous(), relu=True)
+    return y.permute(0, 3, 1, 2)
+
+
+class ResNet34Backbone(nn.Module):
+    def __init__(self, out_channels=1024):
+        super().__init__()
+        self.trunk, self.neck = ResNet34Trunk(), nn.Conv2d(512, out_channels, 1)
+
+    def forward(self, x):
+        if self.training or torch.is_grad_enabled():
+            return [self.neck(self.trunk(x))]
+        t = self.trunk   # inference: BN folded, ReLU / residual add in the convolution epilogue
+        x = _stem(x, t.conv1, t.bn1)
+        for layer in (t.layer1, t.layer2, t.layer3, t.layer4):
+            for blk in layer:
+                idt = x if blk.downsample is None else _conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False)
+                x = _conv_bn_act(_conv_bn_act(x, blk.conv1, blk.bn1), blk.conv2, blk.bn2, residual=idt)
+        return [F.conv2d(x, _cached(self.neck.weight, x.dtype), _cached(self.neck.bias, x.dtype))]
+
+
+# ----------------------------------------------------------------------------------------------------------
+# the model
+# ----------------------------------------------------------------------------------------------------------
+class PoseNet(nn.Module):
+    def __init__(self, cfg: PoseNetConfig | None = None, backbone: nn.Module | None = None):
+        super().__init__()
+        self.cfg = cfg or PoseNetConfig()
+        feature_channel = 1024
+        self.backbone = backbone if backbone is not None else ResNet34Backbone(feature_channel)
+        self.xyz_nocs_head = TopDownXyzHead(in_dim=feature_channel, xyz_num_classes=1)
+        self.size_head = SizeHead(feature_channel, self.cfg.size_head_out_dim, self.cfg.feat_ts)
+        self.nocs_encoder = MAPEncoder(3, featdim=256)
+        self.feat_reducer = nn.Conv2d(feature_channel, 256, kernel_size=1)
+        self.xyz_deform_head = TopDownXyzHead(in_dim=512, xyz_num_classes=1)
+        self.pnp_net = ConvPnPNet(5, featdim=128, rot_dim=4 if "quat" in self.cfg.r_type else 6)
+        self.out_res, self.ROT_TYPE, self.TRANS_TYPE, self.Z_TYPE = self.cfg.out_res, self.cfg.r_type, "centroid_z", "REL"
+        if "rot6d" not in self.cfg.r_type:
+            raise NotImplementedError("GIVEPose's config uses r_type='allo_rot6d' (config/config.py)")
+        self.to(memory_format=torch.channels_last)   # 4-D weights in the layout cuDNN consumes for channel-last activations
+
+    @contextlib.contextmanager
+    def _precision(self):
+        """fp32: TF32 off (the 1e-4 parity mode).  bf16: inference runs on cached bf16 weight copies with bf16 activations
+        (no autocast re-casting); under autograd (training step) it is autocast over the fp32 master weights."""
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        if self.cfg.precision == "fp32":
+            torch.backends.cudnn.allow_tf32 = False
+            torch.backends.cuda.matmul.allow_tf32 = False
+        try:
+            if self.cfg.precision == "bf16" and torch.is_grad_enabled():
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    yield
+            else:
+                yield
+        finally:
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+    def forward(self, data, device, do_loss=False, pred_scale=None):
+        dev = torch.device(device)
+        if dev.type != "cuda":
+            raise RuntimeError("givepose_b200.PoseNet: Not implemented on the CPU (there is no CPU fallback)")
+        img = data["roi_img"].to(dev, non_blocking=True)
+        mask = data["roi_mask_deform" if do_loss else "roi_mask"].to(dev, non_blocking=True)
+        # Resize(out_res, NEAREST) of the square mask: src index = floor(dst * in/out) (PoseNet.py:170,180)
+        step = mask.shape[-1] // self.out_res
+        mask_out = mask[..., ::step, ::step] if mask.shape[-1] % self.out_res == 0 else F.interpolate(mask, size=self.out_res, mode="nearest")
+        if self.cfg.precision == "bf16" and not torch.is_grad_enabled():
+            img = img.to(torch.bfloat16)
+        with self._precision():
+            feat = self.backbone(img.contiguous(memory_format=torch.channels_last))
+            f_nhwc = feat[0].permute(0, 2, 3, 1)                              # (B, 8, 8, 1024) channel-last view
+            if not f_nhwc.is_contiguous():
+                f_nhwc = f_nhwc.contiguous()
+            pred_size = self.size_head(feat).float()
+            nocs = self.xyz_nocs_head.forward_nhwc(f_nhwc)                    # (B, 64, 64, 3)
+            nocs_feat = self.nocs_encoder.forward_nhwc(nocs)                  # (B, 8, 8, 256)
+            conv_feat256 = _conv1x1_rows(f_nhwc, self.feat_reducer)
+            ivfc = self.xyz_deform_head.forward_nhwc(torch.cat([conv_feat256, nocs_feat.to(conv_feat256.dtype)], dim=-1))
+            coord2d = data["roi_coord_2d"].to(dev, non_blocking=True).permute(0, 2, 3, 1)
+            rot6, t, _ = self.pnp_net.forward_nhwc(torch.cat([ivfc, coord2d.to(ivfc.dtype)], dim=-1))
+        coor_xyz_nocs = nocs.float().permute(0, 3, 1, 2)
+        coor_xyz_ivfc = ivfc.float().permute(0, 3, 1, 2)
+        mean_size = data["mean_size"].to(dev)
+        pred_size = pred_size + mean_size / mean_size.norm(dim=1).unsqueeze(-1)
+        cams = data["cam_K"].to(dev)
+        is_allo = "allo" in self.ROT_TYPE
+        t = t.float()
+        if self.cfg.t_type != "site":
+            t = torch.cat([t[:, :2] * 0, t[:, 2:3]], 1)
+        args = (cams, data["bbox_center"].to(dev), data["roi_wh"].to(dev), data["resize_ratio"].to(dev))
+        if do_loss or torch.is_grad_enabled():
+            rot, trans = _pose_decode_torch(rot6.float(), t, *args, is_allo)   # differentiable (train path, :160-249)
+        else:
+            z_calib = float(cams.reshape(-1, 9)[0, 0]) / 590.0 if self.cfg.dataset == "wild6d" else 1.0
+            rot, trans = ops.pose_decode(rot6.float(), t, cams, *args[1:], is_allo=is_allo, z_calib=z_calib)
+            if self.cfg.rot_on_cpu:
+                rot = rot.cpu()   # one batched D2H instead of the reference's per-RoI loop
+        return {"rot": rot, "trans": trans, "size": pred_size, "mask": mask_out, "nocs_coor": coor_xyz_nocs,
+                "ivfc_coor": coor_xyz_ivfc}
+
+
+def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo):
+    """Differentiable twin of ``ops.pose_decode`` for the training step: ``pose_from_predictions_train``
+    (pose_from_pred_centroid_z.py:160-249) with ``allo_to_ego_mat_torch`` (pose_utils/utils.py:198-229)."""
+    x = F.normalize(rot6[..., 0:3], p=2, dim=-1)
+    z = F.normalize(torch.cross(x, rot6[..., 3:6], dim=-1), p=2, dim=-1)
+    R = torch.stack((x, torch.cross(z, x, dim=-1), z), dim=-1)
+    if cams.dim() == 2:
+        cams = cams.unsqueeze(0)
+    cx = t[:, 0:1] * whs[:, 0:1] + centers[:, 0:1]
+    cy = t[:, 1:2] * whs[:, 1:2] + centers[:, 1:2]
+    zz = t[:, 2:3] * ratios.view(-1, 1)
+    trans = torch.cat([zz * (cx - cams[:, 0:1, 2]) / cams[:, 0:1, 0], zz * (cy - cams[:, 1:2, 2]) / cams[:, 1:2, 1], zz], 1)
+    if is_allo:
+        ray = trans / (trans.norm(dim=1, keepdim=True) + 1e-4)
+        cam_ray = torch.tensor([0.0, 0.0, 1.0], device=t.device).expand_as(ray)
+        angle = torch.acos((cam_ray * ray).sum(1).clamp(-1, 1))
+        axis = F.normalize(torch.cross(cam_ray, ray, dim=1) + 1e-8, dim=1)
+        c, s = torch.cos(angle), torch.sin(angle)
+        K = torch.zeros(t.shape[0], 3, 3, device=t.device)
+        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
+        K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
+        M = torch.eye(3, device=t.device) + s[:, None, None] * K + (1 - c)[:, None, None] * (K @ K)
+        R = M @ R
+    return R, trans

@@ -117,6 +117,36 @@ int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void
 /* releases the device scratch cached by the *_host entry points */
 int gp_host_cache_release(void);
 
+/* ---- PoseNet forward: fused glue kernels around the core (fp32 parameters, activations of `dtype`) -------- */
+
+/* x1 = GELU(LayerNorm_eps(DWConv3x3_pad1(x) + bias)) of the DCNv3 module (modules/dcnv3.py:269-283,329), channel-last
+ * (N,H,W,C), C in {128,256,512}.  Only the first `rows` pixels of the flat N*H*W pixel list are computed -- the core
+ * reads offset/mask through their flat N*Ho*Wo-row prefix, so the stride-2 in-model calls need a quarter of x1.
+ * w_t: depthwise weights transposed to [9][C] (tap-major: w_t[(ky*3+kx)*C + c] = weight[c,0,ky,kx]). */
+int gp_dwconv3x3_ln_gelu(const void *x, const float *w_t, const float *bias, const float *ln_w, const float *ln_b,
+                         void *out, int N, int H, int W, int C, long long rows, float eps, int dtype, void *stream);
+
+/* y = act(GroupNorm_G(x)) on channel-last (N,H,W,C) activations (layer_utils.py:32-60 "GN", conv_module.py order
+ * conv -> norm -> act); act: 0 none, 1 ReLU, 2 exact GELU.  stats: N*G*2 floats of scratch (zeroed by the call). */
+int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, const float *beta, int N, int H, int W,
+                     int C, int G, float eps, int act, int dtype, void *stream);
+
+/* nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) of TopDownXyzHead (xyz_head.py:262-265) on channel-last
+ * activations: (N,H,W,C) -> (N,2H,2W,C). */
+int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream);
+
+/* MaxPool2d(3, stride 2, pad 1) on channel-last activations (stem of the stand-in ResNet backbone, resnet.py:106):
+ * (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C).  relu != 0 computes maxpool(relu(x)) (= relu(maxpool(x))) in the same pass. */
+int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream);
+
+/* rot6 (B,6) + t (B,3: centroid dx, dy, relative z) -> ego rotation (B,3,3) and translation (B,3):
+ * rot6d_to_mat_batch (rot_reps.py:34-55), back-projection (pose_from_pred_centroid_z.py:78-119, z_type REL,
+ * z_calib = fx/590 for wild6d else 1) and the allocentric->egocentric rotation (pose_utils/utils.py:29-60) that the
+ * reference runs in a per-RoI host loop (:139-157).  cam: (B,3,3) if cam_batched else (3,3). */
+int gp_pose_decode(const float *rot6, const float *t, const float *cam, int cam_batched, const float *centers,
+                   const float *whs, const float *ratios, float *rot_out, float *trans_out, int B, int is_allo,
+                   float z_calib, void *stream);
+
 /* Tiling of the sampling kernels: output-tile height/width, groups per CTA and channels per lane for
  * 16-bit storage in the forward kernel (4 or 8); values <= 0 keep the current setting; tile sizes are rounded
  * down to powers of two; defaults 8, 8, 2, 8; also read once from

@@ -1,0 +1,155 @@
+"""GPU parity of the PoseNet forward path: fused glue kernels vs plain torch, and the whole
+``givepose_b200.posenet.PoseNet.forward`` vs the golden outputs of the reference ``PoseNet.forward`` / the CPU oracle.
+
+Tolerances: fp32 -> 1e-4 relative to each output's max magnitude (north_star); bf16 -> BF16_TOL, stated below."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "posenet.npz"))
+KEYS = ("rot", "trans", "size", "nocs_coor", "ivfc_coor")
+FP32_TOL = 1e-4
+BF16_TOL = 1e-1   # bf16 weights + activations (8 mantissa bits) through ~60 layers; measured 1e-2 .. 6e-2, relative to each output's max magnitude
+
+
+def rel(a, b):
+    a, b = torch.as_tensor(a).double().cpu(), torch.as_tensor(b).double().cpu()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+@pytest.fixture(scope="module")
+def OP():
+    from oracle import posenet
+    return posenet
+
+
+def build(OP, mode, precision="fp32"):
+    from givepose_b200.posenet import PoseNet, PoseNetConfig
+    ora = OP.PoseNet().eval()
+    OP.init_weights(ora, mode, seed=0)
+    net = PoseNet(PoseNetConfig(precision=precision)).eval()
+    net.load_state_dict(ora.state_dict(), strict=True)
+    return ora, net.cuda()
+
+
+@pytest.mark.parametrize("C,N,H,W,rows", [(256, 4, 16, 16, None), (256, 8, 32, 32, 8 * 16 * 16), (128, 2, 7, 9, 50), (512, 1, 5, 5, None)])
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dwconv_ln_gelu_matches_torch(C, N, H, W, rows, dtype):
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(N, H, W, C, generator=g)
+    w = torch.randn(C, 1, 3, 3, generator=g) * 0.3
+    b, lw, lb = torch.randn(C, generator=g) * 0.1, torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    xq = x.to(dtype).float()
+    ref = F.gelu(F.layer_norm(F.conv2d(xq.permute(0, 3, 1, 2), w, b, padding=1, groups=C).permute(0, 2, 3, 1), (C,), lw, lb, 1e-6))
+    ref = ref.reshape(-1, C)[: (rows or N * H * W)]
+    got = ops.dwconv3x3_ln_gelu(x.to("cuda", dtype), w.reshape(C, 9).t().contiguous().cuda(), b.cuda(), lw.cuda(), lb.cuda(), rows)
+    assert got.shape == ref.shape
+    assert rel(got, ref) < (2e-6 if dtype == torch.float32 else 8e-3)
+
+
+@pytest.mark.parametrize("act", ["none", "relu", "gelu"])
+@pytest.mark.parametrize("up", [False, True])
+@pytest.mark.parametrize("shape", [(3, 16, 16, 256), (2, 8, 8, 128), (1, 5, 7, 256), (20, 4, 4, 128)])
+def test_groupnorm_act_matches_torch(act, up, shape):
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(*shape, generator=g) * 2 + 0.5
+    C = shape[-1]
+    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    y = F.group_norm(x.permute(0, 3, 1, 2), 32, gam, bet, 1e-5)
+    y = F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
+    if up:
+        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+    got = ops.groupnorm_act(x.cuda(), gam.cuda(), bet.cuda(), 32, 1e-5, act, up)
+    assert rel(got, y.permute(0, 2, 3, 1)) < 5e-6
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_maxpool_and_upsample_match_torch(dtype):
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 13, 10, 64, generator=g).to(dtype)
+    ref = F.max_pool2d(x.float().permute(0, 3, 1, 2), 3, 2, 1).permute(0, 2, 3, 1)
+    assert torch.equal(ops.maxpool3x3s2(x.cuda()).float().cpu(), ref)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    assert rel(ops.upsample_bilinear2x(x.cuda()), up) < (2e-6 if dtype == torch.float32 else 8e-3)
+
+
+def test_pose_decode_matches_oracle(OP):
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    B = 257
+    rot6, t = torch.randn(B, 6, generator=g), torch.randn(B, 3, generator=g) * 0.3
+    t[:, 2] = t[:, 2].abs() + 0.5
+    t[0, :2] = 0   # exercise the near-axis ray
+    d = OP.make_inputs(B, seed=1)
+    r_ref, tr_ref = OP.pose_from_predictions_test(OP.rot6d_to_mat(rot6), t[:, :2], t[:, 2:3], d["cam_K"], d["bbox_center"],
+                                                  d["resize_ratio"], d["roi_wh"])
+    for cam in (d["cam_K"], d["cam_K"][0]):
+        r, tr = ops.pose_decode(rot6.cuda(), t.cuda(), cam.cuda(), d["bbox_center"].cuda(), d["roi_wh"].cuda(), d["resize_ratio"].cuda())
+        assert rel(tr, tr_ref) < 1e-6 and (r.cpu() - r_ref).abs().max().item() < 2e-6
+
+
+def test_dcnv3_module_fused_equals_unfused(OP):
+    """The rows-prefix / fused-softmax inference path computes what the reference op sequence computes."""
+    from givepose_b200.posenet import DCNv3
+    torch.manual_seed(0)
+    m = DCNv3(256, kernel_size=3, stride=2, group=4).cuda()
+    with torch.no_grad():
+        for lin in (m.offset, m.mask):
+            lin.weight.normal_(std=0.08)
+            lin.bias.normal_(std=0.3)
+    x = torch.randn(8, 32, 32, 256, device="cuda")
+    with torch.no_grad():
+        fused = m(x)
+    with torch.enable_grad():
+        unfused = m(x.clone().requires_grad_(True))
+    assert fused.shape == (8, 16, 16, 256) and rel(fused, unfused.detach()) < 2e-5
+    unfused.square().mean().backward()   # the training path is differentiable end to end
+
+
+@pytest.mark.parametrize("mode", ["reference", "o1"])
+def test_posenet_fp32_matches_reference_golden(OP, mode):
+    ora, net = build(OP, mode)
+    data = OP.make_inputs(8, seed=0)
+    with torch.no_grad():
+        out = net(data, "cuda")
+    assert out["rot"].device.type == "cpu" and out["trans"].is_cuda   # reference devices (pose_from_pred_centroid_z.py:157)
+    assert set(out) == {"rot", "trans", "size", "mask", "nocs_coor", "ivfc_coor"}
+    for k in KEYS:
+        assert tuple(out[k].shape) == GOLD[f"{mode}/{k}"].shape, k
+        assert rel(out[k], GOLD[f"{mode}/{k}"]) < FP32_TOL, (mode, k, rel(out[k], GOLD[f"{mode}/{k}"]))
+    assert torch.equal(out["mask"].cpu(), data["roi_mask"][:, :, ::4, ::4])
+
+
+def test_posenet_bf16_within_stated_tolerance(OP):
+    ora, net = build(OP, "o1", precision="bf16")
+    data = OP.make_inputs(8, seed=0)
+    with torch.no_grad():
+        out = net(data, "cuda")
+    for k in KEYS:
+        assert rel(out[k], GOLD[f"o1/{k}"]) < BF16_TOL, (k, rel(out[k], GOLD[f"o1/{k}"]))
+
+
+def test_posenet_shard_equals_oracle_on_the_shard(OP):
+    """RoI sharding: a rank's result is the reference's result on that rank's sub-batch."""
+    ora, net = build(OP, "o1")
+    data = OP.make_inputs(8, seed=0)
+    shard = {k: v[4:] for k, v in data.items()}
+    with torch.no_grad():
+        ref = ora(shard)
+        out = net(shard, "cuda")
+    for k in KEYS:
+        assert rel(out[k], ref[k]) < FP32_TOL, k
+
+
+def test_posenet_refuses_cpu(OP):
+    from givepose_b200.posenet import PoseNet
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        PoseNet().eval()(OP.make_inputs(1), "cpu")
