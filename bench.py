@@ -123,6 +123,146 @@ def time_cpu_port(n_sample, steps, warmup, dist):
     return (fwd + bwd) / dt / 1e9, dt, torch.get_num_threads()
 
 
+# ---- PoseNet RoIs/s (BASELINE configs[2..3]) ---------------------------------------------------------------
+# per-RoI algorithmic FLOPs (2*MAC): decoders 12.99 + 12.84 G, MAPEncoder 1.40 G, ConvPnPNet 0.14 G,
+# feat_reducer 0.034 G, ResNet-34 trunk @256^2 ~ 7.34 G (+ neck 0.067 G)
+POSENET_GFLOP_PER_ROI = 12.99 + 12.84 + 1.40 + 0.14 + 0.034 + 7.34 + 0.067
+
+
+def build_posenet(precision, device, seed=0):
+    """Random-init weights of the reference architecture (oracle.posenet.init_weights 'o1': O(1) activations, offsets of a
+    few pixels) -- building the checker's weights is not using it; the timed model is givepose_b200.posenet.PoseNet."""
+    from givepose_b200.posenet import PoseNet, PoseNetConfig
+    from oracle import posenet as OP
+    ora = OP.PoseNet().eval()
+    OP.init_weights(ora, "o1", seed=seed)
+    net = PoseNet(PoseNetConfig(precision=precision)).eval()
+    net.load_state_dict(ora.state_dict(), strict=True)
+    return ora, net.to(device)
+
+
+def posenet_inputs(B, seed):
+    from oracle import posenet as OP
+    return OP.make_inputs(B, seed=seed)
+
+
+def time_posenet_cpu(B, steps):
+    """Reference CPU path (oracle port of PoseNet.forward) on all host threads; returns RoIs/s."""
+    from oracle import posenet as OP
+    torch.set_num_threads(os.cpu_count() or 1)
+    ora = OP.PoseNet().eval()
+    OP.init_weights(ora, "o1", seed=0)
+    data = OP.make_inputs(B, seed=0)
+    with torch.no_grad():
+        ora(data)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            ora(data)
+            ts.append(time.perf_counter() - t0)
+    dt = sum(ts) / len(ts)
+    return B / dt, dt, torch.get_num_threads()
+
+
+def run_posenet(args, rank, world, dev, dist):
+    """RoI-sharded inference: the batch of args.posenet_rois synthetic RoIs is split into contiguous shards, one per rank,
+    each rank owns a full weight replica, no collective on the data path -> strong scaling."""
+    total = args.posenet_rois
+    if total % world:
+        raise SystemExit(f"--posenet-rois {total} must divide by the world size {world}")
+    B = total // world
+    out = {"metric": "posenet_inference_rois_per_s", "unit": "RoIs/s", "batch_rois": total, "rois_per_rank": B,
+           "scaling": "strong", "backbone": "ResNet-34 trunk + 1x1 neck (stand-in for timm ConvNeXt-B, needs the network)",
+           "weights": "random init (oracle.posenet.init_weights 'o1')", "gflop_per_roi": round(POSENET_GFLOP_PER_ROI, 2)}
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    host = posenet_inputs(B, seed=rank)                      # this rank's shard, generated on the host
+    pinned = {k: v.pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in host.items()}
+    for prec in (["bf16", "fp32"] if args.posenet_fp32 else ["bf16"]):
+        _, net = build_posenet(prec, dev)
+        steps = args.posenet_steps if prec == "bf16" else max(1, args.posenet_steps // 3)
+        with torch.no_grad():
+            for _ in range(3):
+                net(resident, dev)
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                res = net(resident, dev)
+            e1.record()
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+            # end to end: pinned host inputs -> H2D inside forward (as the reference does, PoseNet.py:174-211) -> D2H of the poses
+            net(pinned, dev)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                res = net(pinned, dev)
+                pose = (res["rot"], res["trans"].cpu(), res["size"].cpu())   # rot is already on the host (reference behaviour)
+            barrier()
+            te = torch.tensor([(time.perf_counter() - t0) / steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.item(), te.item() * 1e3
+        nb = lambda x: x.numel() * x.element_size()
+        entry = {"value": round(total / (ms * 1e-3), 1), "ms_per_batch": round(ms, 3), "steps": steps,
+                 "tflops": round(total / (ms * 1e-3) * POSENET_GFLOP_PER_ROI / 1e3, 1),
+                 "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "RoIs/s", "ms_per_batch": round(ms_e2e, 3),
+                         "h2d_bytes_per_step": sum(nb(v) for v in host.values()) * world,
+                         "d2h_bytes_per_step": sum(nb(x) for x in pose) * world,
+                         "api": "givepose_b200.posenet.PoseNet.forward(data on pinned host memory, device)"}}
+        if prec == "bf16":
+            peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+            peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1383.2) if os.path.exists(peaks_path) else 1383.2
+            entry["roofline"] = {"bound": "tensor", "achieved": entry["tflops"], "peak": peak * world, "unit": "TFLOP/s",
+                                 "frac": round(entry["tflops"] / (peak * world), 4),
+                                 "note": "whole forward (library convs/GEMMs + our glue kernels) vs sustained bf16 GEMM peak"}
+            out.update({"value": entry["value"], "dtype": "bf16", **{k: v for k, v in entry.items() if k != "value"}})
+        else:
+            out["fp32_parity_mode"] = entry
+        del net
+        torch.cuda.empty_cache()
+    if args.train_rois > 0:
+        # BASELINE configs[4]: data-parallel training step, `train_rois` RoIs per GPU (reference batch_size 48, config.py:42),
+        # bf16 autocast over fp32 master weights, ONE NCCL all-reduce of the flat fp32 gradient bucket per step
+        from givepose_b200.train import GradBucket, make_targets, train_step
+        _, net = build_posenet("bf16", dev)
+        tb = args.train_rois
+        tdata = {k: v.to(dev) for k, v in posenet_inputs(tb, seed=100 + rank).items()}
+        tgt = make_targets(tb, dev, seed=rank)
+        opt = torch.optim.SGD(net.parameters(), lr=1e-5, momentum=0.9)
+        bucket = GradBucket(net.parameters())
+        for _ in range(2):
+            train_step(net, tdata, tgt, opt, bucket, dev)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.posenet_steps):
+            loss = train_step(net, tdata, tgt, opt, bucket, dev)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1) / args.posenet_steps], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        out["train_step"] = {"value": round(tb * world / (t.item() * 1e-3), 1), "unit": "RoIs/s", "rois_per_gpu": tb, "scaling": "weak",
+                             "ms_per_step": round(t.item(), 3), "dtype": "bf16 autocast, fp32 master weights + grads",
+                             "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum)/world, one flat bucket" if world > 1 else "none (1 rank)",
+                             "loss": "surrogate L1 / smooth-L1 (reference PoseLoss is out of scope this round)", "last_loss": round(float(loss), 5)}
+        del net, opt, bucket
+        torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rps, dt, threads = time_posenet_cpu(8, 2)
+        out["cpu_baseline"] = {"value": round(rps, 3), "unit": "RoIs/s", "cores": threads, "kind": "port",
+                               "sample": f"oracle.posenet.PoseNet.forward (fp32, CPU), B=8 RoIs, 1 warm-up + 2 timed, {dt:.2f} s/batch"}
+    return out
+
+
 def run_reference(args, rank):
     """Reference arm: the reference's CPU implementation of the path (oracle port; the Python reference cannot
     travel to the GPU box and its CUDA extension has no CPU path, src/dcnv3.h:37) on rank 0, all host threads."""
@@ -141,6 +281,12 @@ def run_reference(args, rank):
         "e2e": {"value": round(gbps, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if not args.no_posenet:
+        rps, dtp, th = time_posenet_cpu(8, max(1, min(args.steps, 3)))
+        line["posenet"] = {"metric": "posenet_inference_rois_per_s", "value": round(rps, 3), "unit": "RoIs/s", "dtype": "f32",
+                           "cpu_baseline": {"value": round(rps, 3), "unit": "RoIs/s", "cores": th, "kind": "port",
+                                            "sample": f"oracle.posenet.PoseNet.forward on CPU, B=8 RoIs per step, {dtp:.2f} s/step"},
+                           "e2e": {"value": round(rps, 3), "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
@@ -154,6 +300,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-posenet", action="store_true", help="skip the PoseNet RoIs/s section")
+    ap.add_argument("--posenet-rois", type=int, default=4096, help="RoIs per batch, sharded across the ranks (BASELINE configs[3])")
+    ap.add_argument("--posenet-steps", type=int, default=5)
+    ap.add_argument("--posenet-fp32", action="store_true", help="also time the fp32 (TF32 off) parity mode")
+    ap.add_argument("--train-rois", type=int, default=48, help="RoIs per GPU of the training-step config (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -268,6 +419,12 @@ def main():
                "steps": e2e_steps, "api": "gp_dcnv3_forward_host + gp_dcnv3_backward_host (pinned host buffers)"}
         lib.gp_host_cache_release()
 
+    posenet = None
+    if not args.no_posenet:
+        launches_before = int(lib.gp_launch_count())
+        posenet = run_posenet(args, rank, world, dev, dist)
+        posenet["gpu_launches_total"] = int(lib.gp_launch_count()) - launches_before
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -306,7 +463,7 @@ def main():
                                "(BASELINE configs[1])", "dist": args.dist, "parallelism": f"roi-shard x{world}, no collective",
                    "l2": "no flush needed: 763 MB of inputs per step >> 126 MB L2",
                    "algorithmic_bytes_per_step": fwd_b + bwd_b},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks,
+        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "posenet": posenet,
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(line), flush=True)

@@ -552,9 +552,10 @@ class PoseNet(nn.Module):
                 "ivfc_coor": coor_xyz_ivfc}
 
 
-def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo):
+def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo, eps=1e-4):
     """Differentiable twin of ``ops.pose_decode`` for the training step: ``pose_from_predictions_train``
-    (pose_from_pred_centroid_z.py:160-249) with ``allo_to_ego_mat_torch`` (pose_utils/utils.py:198-229)."""
+    (pose_from_pred_centroid_z.py:160-249) with ``allo_to_ego_mat_torch`` (pose_utils/utils.py:198-229: ray and axis are
+    normalised with ``+ eps``, the rotation goes through a quaternion, ``pose_utils.py:348-412``)."""
     x = F.normalize(rot6[..., 0:3], p=2, dim=-1)
     z = F.normalize(torch.cross(x, rot6[..., 3:6], dim=-1), p=2, dim=-1)
     R = torch.stack((x, torch.cross(z, x, dim=-1), z), dim=-1)
@@ -565,14 +566,16 @@ def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo):
     zz = t[:, 2:3] * ratios.view(-1, 1)
     trans = torch.cat([zz * (cx - cams[:, 0:1, 2]) / cams[:, 0:1, 0], zz * (cy - cams[:, 1:2, 2]) / cams[:, 1:2, 1], zz], 1)
     if is_allo:
-        ray = trans / (trans.norm(dim=1, keepdim=True) + 1e-4)
-        cam_ray = torch.tensor([0.0, 0.0, 1.0], device=t.device).expand_as(ray)
-        angle = torch.acos((cam_ray * ray).sum(1).clamp(-1, 1))
-        axis = F.normalize(torch.cross(cam_ray, ray, dim=1) + 1e-8, dim=1)
-        c, s = torch.cos(angle), torch.sin(angle)
-        K = torch.zeros(t.shape[0], 3, 3, device=t.device)
-        K[:, 0, 1], K[:, 0, 2], K[:, 1, 0] = -axis[:, 2], axis[:, 1], axis[:, 2]
-        K[:, 1, 2], K[:, 2, 0], K[:, 2, 1] = -axis[:, 0], -axis[:, 1], axis[:, 0]
-        M = torch.eye(3, device=t.device) + s[:, None, None] * K + (1 - c)[:, None, None] * (K @ K)
-        R = M @ R
+        ray = trans / (trans.norm(dim=1, keepdim=True) + eps)
+        angle = ray[:, 2:3].acos()
+        cam_ray = torch.tensor([0.0, 0.0, 1.0], dtype=trans.dtype, device=trans.device).expand_as(ray)
+        axis = torch.cross(cam_ray, ray, dim=-1)
+        axis = axis / (axis.norm(dim=1, keepdim=True) + eps)
+        q = torch.cat([torch.cos(angle / 2.0), axis * torch.sin(angle / 2.0)], dim=1)
+        q = q / q.norm(p=2, dim=1, keepdim=True)
+        w, qx, qy, qz = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        X, Y, Z = 2 * qx, 2 * qy, 2 * qz
+        M = torch.stack([1 - (qy * Y + qz * Z), qx * Y - w * Z, qx * Z + w * Y, qx * Y + w * Z, 1 - (qx * X + qz * Z),
+                         qy * Z - w * X, qx * Z - w * Y, qy * Z + w * X, 1 - (qx * X + qy * Y)], dim=1).reshape(-1, 3, 3)
+        R = torch.matmul(M, R)
     return R, trans

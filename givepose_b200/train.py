@@ -1,0 +1,102 @@
+"""Data-parallel plumbing for the PoseNet path: RoI sharding (inference, no collective) and the training step's
+gradient all-reduce (the only collective on the path).
+
+The reference is single-process (``engine/train.py:26,35``); its step is ``forward(do_loss=True) -> loss -> backward ->
+clip_grad_norm_(5) -> optimizer.step()`` (``:117-129``).  Here every rank holds a full replica and a contiguous shard of
+the RoI batch; one bucketed ``all_reduce(sum) / world`` over a flat fp32 buffer sits between ``backward()`` and the
+clip / step.  Backend comes from the process group: NCCL over NVLink on the GPUs, gloo in the CPU tests.
+BatchNorm statistics stay per rank (the reference has no SyncBN in use); parameters that never receive a gradient
+(``DCNv3_C.bn``, built but unused, ``network/dcnv3.py:29,37``) are tolerated.
+"""
+from __future__ import annotations
+
+from typing import Dict, Iterable, Tuple
+
+import torch
+import torch.distributed as dist
+import torch.nn.functional as F
+
+
+def shard_range(total: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous RoI shard of ``rank``; shards differ by at most one RoI (remainder goes to the low ranks)."""
+    if not (0 <= rank < world) or total < 0:
+        raise ValueError(f"bad shard request: total={total} rank={rank} world={world}")
+    base, rem = divmod(total, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(data: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[str, torch.Tensor]:
+    """Slice every per-RoI tensor of the input dict (``datasets/load_data_nocs.py:355-386`` layout).  A camera matrix given
+    once as (3,3) is shared.  NOTE: the stride-2 DCNv3 calls couple RoIs inside a batch, so a shard's
+    results equal the reference run on that shard, not a slice of the reference run on the whole batch."""
+    n = next(v.shape[0] for k, v in data.items() if k != "cam_K" or v.dim() == 3)
+    lo, hi = shard_range(n, rank, world)
+    return {k: (v if (k == "cam_K" and v.dim() == 2) else v[lo:hi]) for k, v in data.items()}
+
+
+class GradBucket:
+    """One flat fp32 buffer for all trainable parameters' gradients -> a single all-reduce per step."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter]):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("GradBucket: no trainable parameters")
+        self.numel = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.params[0].device)
+        self.views, o = [], 0
+        for p in self.params:
+            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            o += p.numel()
+
+    def nbytes(self) -> int:
+        return self.numel * 4
+
+    @torch.no_grad()
+    def allreduce_(self, group=None) -> None:
+        """grads -> flat buffer (zeros where ``grad is None``) -> all_reduce(sum) / world -> back into ``p.grad``."""
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                v.zero_()
+            else:
+                v.copy_(p.grad)
+        if world > 1:
+            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
+            self.flat.div_(world)
+        for p, v in zip(self.params, self.views):
+            if p.grad is None:
+                p.grad = v.clone()
+            else:
+                p.grad.copy_(v)
+
+
+def surrogate_loss(out: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> torch.Tensor:
+    """Stand-in for the reference ``PoseLoss`` (``losses/pose_loss.py:30-96``, out of scope this round):
+    L1 on rot / trans / size and smooth-L1 on the two coordinate maps -- every head and the DCNv3 backward get gradients."""
+    return (F.l1_loss(out["rot"], target["rot"]) + F.l1_loss(out["trans"], target["trans"]) + F.l1_loss(out["size"], target["size"])
+            + F.smooth_l1_loss(out["nocs_coor"], target["nocs_coor"]) + F.smooth_l1_loss(out["ivfc_coor"], target["ivfc_coor"]))
+
+
+def make_targets(B: int, device, seed: int = 0) -> Dict[str, torch.Tensor]:
+    g = torch.Generator().manual_seed(2000 + seed)
+    r = lambda *s: torch.randn(*s, generator=g)
+    q, _ = torch.linalg.qr(r(B, 3, 3))
+    return {k: v.to(device) for k, v in {"rot": q, "trans": r(B, 3) * 0.3, "size": r(B, 3) * 0.1 + 0.5,
+                                         "nocs_coor": r(B, 3, 64, 64) * 0.3, "ivfc_coor": r(B, 3, 64, 64) * 0.3}.items()}
+
+
+def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: float = 5.0, group=None) -> float:
+    """One data-parallel step on this rank's shard: forward (autograd path: torch CUDA ops around ``DCNv3Function``) ->
+    loss -> backward (DCNv3 backward kernel) -> gradient all-reduce -> clip (``engine/train.py:126``) -> step."""
+    net.train()
+    optimizer.zero_grad(set_to_none=True)
+    data = dict(data)
+    data.setdefault("roi_mask_deform", data["roi_mask"])
+    out = net(data, device, do_loss=True)
+    loss = surrogate_loss(out, target)
+    loss.backward()
+    bucket.allreduce_(group)
+    torch.nn.utils.clip_grad_norm_(bucket.params, clip)
+    optimizer.step()
+    return loss.detach()

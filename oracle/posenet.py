@@ -56,6 +56,8 @@ class _LNChannelsLast(nn.Sequential):
 
 
 class DCNv3(nn.Module):
+    differentiable = False   # True: core = dcnv3_core_torch (grid_sample, autograd) on the flat-sliced offset / mask
+
     def __init__(self, channels, kernel_size=3, stride=1, pad=1, dilation=1, group=4, offset_scale=1.0):
         super().__init__()
         self.channels, self.kernel_size, self.stride, self.pad, self.dilation = channels, kernel_size, stride, pad, dilation
@@ -75,8 +77,13 @@ class DCNv3(nn.Module):
         offset = self.offset(x1)
         mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(xp.dtype)
         k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
-        y = core.forward(xp.contiguous(), offset.contiguous(), mask.contiguous(), k, k, s, s, p, p, d, d, self.group,
-                         self.group_channels, self.offset_scale, 0)
+        if self.differentiable:
+            Ho, Wo = core.out_size(H, k, s, p, d), core.out_size(W, k, s, p, d)
+            y = core.dcnv3_core_torch(xp, core.flat_slice(offset.contiguous(), N, Ho, Wo), core.flat_slice(mask.contiguous(), N, Ho, Wo),
+                                      k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale, 0)
+        else:
+            y = core.forward(xp.contiguous(), offset.contiguous(), mask.contiguous(), k, k, s, s, p, p, d, d, self.group,
+                             self.group_channels, self.offset_scale, 0)
         return self.output_proj(y)
 
 
@@ -254,6 +261,31 @@ def pose_from_predictions_test(rots, centroids, z_vals, cams, centers, resize_ra
     return torch.from_numpy(ego), trans
 
 
+def quat2mat(q):   # pose_utils/pose_utils.py:348-412 (eps = 0)
+    q = q / q.norm(p=2, dim=1, keepdim=True)
+    w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+    X, Y, Z = 2 * x, 2 * y, 2 * z
+    return torch.stack([1 - (y * Y + z * Z), x * Y - w * Z, x * Z + w * Y, x * Y + w * Z, 1 - (x * X + z * Z), y * Z - w * X,
+                        x * Z - w * Y, y * Z + w * X, 1 - (x * X + y * Y)], dim=1).reshape(-1, 3, 3)
+
+
+def pose_from_predictions_train(rots, centroids, z_vals, cams, centers, resize_ratios, whs, eps=1e-4):
+    """pose_from_pred_centroid_z.py:160-249 (z_type 'REL', is_allo) + allo_to_ego_mat_torch (pose_utils/utils.py:198-229)."""
+    if cams.dim() == 2:
+        cams = cams.unsqueeze(0)
+    cx = centroids[:, 0:1] * whs[:, 0:1] + centers[:, 0:1]
+    cy = centroids[:, 1:2] * whs[:, 1:2] + centers[:, 1:2]
+    z = z_vals * resize_ratios.view(-1, 1)
+    trans = torch.cat([z * (cx - cams[:, 0:1, 2]) / cams[:, 0:1, 0], z * (cy - cams[:, 1:2, 2]) / cams[:, 1:2, 1], z], 1)
+    cam_ray = torch.tensor([0, 0, 1.0], dtype=trans.dtype, device=trans.device)
+    obj_ray = trans / (torch.norm(trans, dim=1, keepdim=True) + eps)
+    angle = obj_ray[:, 2:3].acos()
+    axis = torch.cross(cam_ray.expand_as(obj_ray), obj_ray, dim=-1)
+    axis = axis / (torch.norm(axis, dim=1, keepdim=True) + eps)
+    q = torch.cat([torch.cos(angle / 2.0), axis * torch.sin(angle / 2.0)], dim=1)
+    return torch.matmul(quat2mat(q), rots), trans
+
+
 # ------------------------------------------------------------------------------------------------------
 # the model
 # ------------------------------------------------------------------------------------------------------
@@ -268,10 +300,9 @@ class PoseNet(nn.Module):
         self.xyz_deform_head = TopDownXyzHead(512)
         self.pnp_net = ConvPnPNet(5, 128)
 
-    def forward(self, data, device="cpu", do_loss=False, pred_scale=None):   # PoseNet.py:173-231, inference branch
-        assert not do_loss, "the oracle restates the inference forward"
+    def forward(self, data, device="cpu", do_loss=False, pred_scale=None):   # PoseNet.py:173-231
         img = data["roi_img"].to(device)
-        mask_out = data["roi_mask"].to(device)[:, :, ::4, ::4]   # Resize(64, NEAREST) of a 256x256 map: src = floor(4*i) (PoseNet.py:170,180)
+        mask_out = data["roi_mask_deform" if do_loss else "roi_mask"].to(device)[:, :, ::4, ::4]   # Resize(64, NEAREST) of a 256x256 map: src = floor(4*i) (PoseNet.py:170,180)
         feat = self.backbone(img)
         pred_size = self.size_head(feat[0])
         nocs = torch.cat(self.xyz_nocs_head(feat[0]), 1)
@@ -281,9 +312,9 @@ class PoseNet(nn.Module):
         rot6, t = self.pnp_net(torch.cat([ivfc, data["roi_coord_2d"].to(device)], 1))
         mean_size = data["mean_size"].to(device)
         pred_size = pred_size + mean_size / mean_size.norm(dim=1).unsqueeze(-1)
-        rot, trans = pose_from_predictions_test(rot6d_to_mat(rot6), t[:, :2], t[:, 2:3], data["cam_K"].to(device),
-                                                data["bbox_center"].to(device), data["resize_ratio"].to(device),
-                                                data["roi_wh"].to(device))
+        decode = pose_from_predictions_train if do_loss else pose_from_predictions_test
+        rot, trans = decode(rot6d_to_mat(rot6), t[:, :2], t[:, 2:3], data["cam_K"].to(device), data["bbox_center"].to(device),
+                            data["resize_ratio"].to(device), data["roi_wh"].to(device))
         return {"rot": rot, "trans": trans, "size": pred_size, "mask": mask_out, "nocs_coor": nocs, "ivfc_coor": ivfc}
 
 

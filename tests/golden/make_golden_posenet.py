@@ -93,6 +93,16 @@ def main():
             print(f"[{mode}] {k:10s} ref absmax {a.abs().max().item():.3e}  oracle-vs-ref rel {rel:.2e}")
             if k != "mask":
                 blob[f"{mode}/{k}"] = out_ref[k].numpy()
+        if mode == "o1":   # training-path pose decode (do_loss=True: pose_from_predictions_train + allo_to_ego_mat_torch)
+            dtrain = {k: v.clone() for k, v in data.items()}
+            dtrain["roi_mask_deform"] = dtrain["roi_mask"].clone()
+            with torch.no_grad():
+                tr_ref = ref.forward({k: v.clone() for k, v in dtrain.items()}, "cpu", do_loss=True)
+                tr_mine = mine.forward(dtrain, "cpu", do_loss=True)
+            for k in ("rot", "trans"):
+                a, b = tr_ref[k].double(), tr_mine[k].double()
+                print(f"[o1 train path] {k:6s} oracle-vs-ref rel {((a - b).abs().max() / a.abs().max()).item():.2e}")
+                blob[f"o1_train/{k}"] = tr_ref[k].numpy()
         blob[f"{mode}/sha_inputs"] = np.array(sha(data[k] for k in sorted(data)))
         blob[f"{mode}/sha_weights"] = np.array(sha(sd[k] for k in sorted(sd)))
     blob["__provenance__"] = np.array(["reference network/PoseNet.py:173-231 forward (CPU, eval), DCNv3 core = reference "

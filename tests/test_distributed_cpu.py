@@ -1,0 +1,72 @@
+"""CPU, world_size 2, gloo: the host logic of the multi-GPU paths -- RoI sharding (no collective) and the gradient
+all-reduce bucket of the training step.  No CUDA compute here; the kernels' N>1 run is `bench.py --gpus N` on the box."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from givepose_b200.train import GradBucket, shard_batch, shard_range
+
+
+def test_shard_ranges_partition_the_batch():
+    for total in (0, 1, 7, 48, 4096, 4099):
+        for world in (1, 2, 3, 4, 8):
+            r = [shard_range(total, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+    assert [shard_range(4096, k, 8) for k in (0, 7)] == [(0, 512), (3584, 4096)]   # multiples of 256 (im2col_step) and of 4
+    with pytest.raises(ValueError):
+        shard_range(8, 2, 2)
+
+
+def test_shard_batch_slices_per_roi_tensors_and_shares_a_single_camera():
+    data = {"roi_img": torch.arange(10.0).view(10, 1), "cam_K": torch.eye(3), "roi_wh": torch.ones(10, 2)}
+    s = shard_batch(data, 1, 3)
+    assert s["roi_img"].flatten().tolist() == [4.0, 5.0, 6.0] and s["cam_K"].shape == (3, 3) and s["roi_wh"].shape == (3, 2)
+    data["cam_K"] = torch.eye(3).repeat(10, 1, 1)
+    assert shard_batch(data, 2, 3)["cam_K"].shape == (3, 3, 3)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)   # identical replicas
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        unused = torch.nn.BatchNorm1d(3)   # never receives a gradient, like DCNv3_C.bn
+        params = list(net.parameters()) + list(unused.parameters())
+        bucket = GradBucket(params)
+        x = torch.arange(24.0).view(4, 6) / 10
+        lo, hi = shard_range(4, rank, world)
+        net(x[lo:hi]).square().sum().backward()
+        bucket.allreduce_()
+        flat = torch.cat([p.grad.flatten() for p in params])
+        # reference: mean over ranks of the per-shard gradients == (sum over all rows) / world
+        ref_net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 2))
+        ref_net.load_state_dict(net.state_dict())
+        ref_net(x).square().sum().backward()
+        ref = torch.cat([p.grad.flatten() for p in ref_net.parameters()] + [torch.zeros(6)]) / world
+        out[rank] = (torch.allclose(flat, ref, atol=1e-6), bucket.nbytes())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_bucket_gloo_world2():
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: (True, (6 * 5 + 5 + 5 * 2 + 2 + 6) * 4), 1: (True, (6 * 5 + 5 + 5 * 2 + 2 + 6) * 4)}
