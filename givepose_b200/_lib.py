@@ -38,6 +38,7 @@ EXPORTS = {
     "gp_dcnv3_sample_index": (_I, [_VP, _VP, _VP, _DP, _I, _VP]),
     "gp_dcnv3_forward_host": (_I, [_VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
     "gp_dcnv3_backward_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I]),
+    "gp_dcnv3_forward_backward_host": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I, _I]),
     "gp_host_cache_release": (_I, []),
     "gp_dwconv3x3_ln_gelu": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _I, _VP]),
     "gp_groupnorm_act": (_I, [_VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _VP]),

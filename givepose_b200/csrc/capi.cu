@@ -333,6 +333,8 @@ struct HostCache {
     void *buf[8] = {nullptr};
     size_t cap[8] = {0};
     cudaStream_t stream = nullptr;
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;   // copy streams of the pipelined forward+backward call
+    cudaEvent_t ev_up[64] = {nullptr}, ev_done[64] = {nullptr};
     int device = -1;
 } g_hc;
 
@@ -370,7 +372,14 @@ int gp_host_cache_release(void) {
         g_hc.cap[i] = 0;
     }
     if (g_hc.stream) cudaStreamDestroy(g_hc.stream);
-    g_hc.stream = nullptr;
+    if (g_hc.s_h2d) cudaStreamDestroy(g_hc.s_h2d);
+    if (g_hc.s_d2h) cudaStreamDestroy(g_hc.s_d2h);
+    for (int i = 0; i < 64; ++i) {
+        if (g_hc.ev_up[i]) cudaEventDestroy(g_hc.ev_up[i]);
+        if (g_hc.ev_done[i]) cudaEventDestroy(g_hc.ev_done[i]);
+        g_hc.ev_up[i] = g_hc.ev_done[i] = nullptr;
+    }
+    g_hc.stream = g_hc.s_h2d = g_hc.s_d2h = nullptr;
     g_hc.device = -1;
     return GP_OK;
 }
@@ -438,6 +447,77 @@ int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void
     if (offset_elems > n_off) memset((char *)h_grad_offset + n_off * es, 0, (offset_elems - n_off) * es);
     if (mask_elems > n_msk) memset((char *)h_grad_mask + n_msk * es, 0, (mask_elems - n_msk) * es);
     GP_CUDA(cudaStreamSynchronize(st));
+    return GP_OK;
+}
+
+int gp_dcnv3_forward_backward_host(const void *h_input, const void *h_offset, const void *h_mask, const void *h_grad_out,
+                                   void *h_out, void *h_grad_input, void *h_grad_offset, void *h_grad_mask,
+                                   size_t offset_elems, size_t mask_elems, const gp_dcnv3_desc *desc, int dtype, int device,
+                                   int chunks) {
+    if (!h_input || !h_offset || !h_mask || !h_grad_out || !h_out || !h_grad_input || !h_grad_offset || !h_grad_mask)
+        return GP_ERR_NULL;
+    const size_t es = elem_size(dtype);
+    if (!es) return GP_ERR_DTYPE;
+    KParams p;
+    if (int e = make_params(desc, p)) return e;
+    const size_t img_in = (size_t)p.H * p.W * p.C, img_out = (size_t)p.Ho * p.Wo * p.C;
+    const size_t img_off = (size_t)p.Ho * p.Wo * p.G * p.P * 2, img_msk = (size_t)p.Ho * p.Wo * p.G * p.P;   // flat prefix per RoI
+    const size_t n_off = img_off * p.N, n_msk = img_msk * p.N;
+    if (offset_elems < n_off || mask_elems < n_msk) return GP_ERR_SHAPE;
+    if (chunks < 1) chunks = 1;
+    if (chunks > 64) chunks = 64;
+    if (chunks > p.N) chunks = p.N;
+    GP_CUDA(hc_begin(device));
+    if (!g_hc.s_h2d) GP_CUDA(cudaStreamCreateWithFlags(&g_hc.s_h2d, cudaStreamNonBlocking));
+    if (!g_hc.s_d2h) GP_CUDA(cudaStreamCreateWithFlags(&g_hc.s_d2h, cudaStreamNonBlocking));
+    for (int c = 0; c < chunks; ++c) {
+        if (!g_hc.ev_up[c]) GP_CUDA(cudaEventCreateWithFlags(&g_hc.ev_up[c], cudaEventDisableTiming));
+        if (!g_hc.ev_done[c]) GP_CUDA(cudaEventCreateWithFlags(&g_hc.ev_done[c], cudaEventDisableTiming));
+    }
+    char *d_in, *d_off, *d_msk, *d_go, *d_gi, *d_goff, *d_gmsk, *d_out;
+    GP_CUDA(hc_get(0, img_in * p.N * es, (void **)&d_in));
+    GP_CUDA(hc_get(1, n_off * es, (void **)&d_off));
+    GP_CUDA(hc_get(2, n_msk * es, (void **)&d_msk));
+    GP_CUDA(hc_get(3, img_out * p.N * es, (void **)&d_go));
+    GP_CUDA(hc_get(4, img_in * p.N * es, (void **)&d_gi));
+    GP_CUDA(hc_get(5, n_off * es, (void **)&d_goff));
+    GP_CUDA(hc_get(6, n_msk * es, (void **)&d_gmsk));
+    const bool half16 = dtype == GP_BF16 || dtype == GP_F16;
+    // slot 7: [forward output | fp32 workspace of the 16-bit backward (one chunk)]
+    const int per = (p.N + chunks - 1) / chunks;
+    const size_t ws_chunk = half16 ? img_in * per * sizeof(float) : 0;
+    GP_CUDA(hc_get(7, img_out * p.N * es + ws_chunk + 256, (void **)&d_out));
+    char *d_ws = half16 ? d_out + ((img_out * p.N * es + 255) / 256) * 256 : nullptr;
+    const char *hi = (const char *)h_input, *ho = (const char *)h_offset, *hm = (const char *)h_mask, *hg = (const char *)h_grad_out;
+    char *ro = (char *)h_out, *rgi = (char *)h_grad_input, *rgo = (char *)h_grad_offset, *rgm = (char *)h_grad_mask;
+    // RoI chunks are independent: the flat offset/mask addressing is linear in the RoI index, so a chunk's rows start at
+    // r0 * (Ho*Wo*G*P) of the same buffers.  H2D of chunk c+1, kernels of chunk c and D2H of chunk c-1 overlap (PCIe is full duplex).
+    for (int c = 0, r0 = 0; c < chunks && r0 < p.N; ++c, r0 += per) {
+        const int n = (r0 + per <= p.N) ? per : p.N - r0;
+        gp_dcnv3_desc dc = *desc;
+        dc.N = n;
+        GP_CUDA(cudaMemcpyAsync(d_in + r0 * img_in * es, hi + r0 * img_in * es, n * img_in * es, cudaMemcpyHostToDevice, g_hc.s_h2d));
+        GP_CUDA(cudaMemcpyAsync(d_off + r0 * img_off * es, ho + r0 * img_off * es, n * img_off * es, cudaMemcpyHostToDevice, g_hc.s_h2d));
+        GP_CUDA(cudaMemcpyAsync(d_msk + r0 * img_msk * es, hm + r0 * img_msk * es, n * img_msk * es, cudaMemcpyHostToDevice, g_hc.s_h2d));
+        GP_CUDA(cudaMemcpyAsync(d_go + r0 * img_out * es, hg + r0 * img_out * es, n * img_out * es, cudaMemcpyHostToDevice, g_hc.s_h2d));
+        GP_CUDA(cudaEventRecord(g_hc.ev_up[c], g_hc.s_h2d));
+        GP_CUDA(cudaStreamWaitEvent(g_hc.stream, g_hc.ev_up[c], 0));
+        if (int e = gp_dcnv3_forward(d_in + r0 * img_in * es, d_off + r0 * img_off * es, d_msk + r0 * img_msk * es,
+                                     d_out + r0 * img_out * es, &dc, dtype, g_hc.stream)) return e;
+        if (int e = gp_dcnv3_backward(d_in + r0 * img_in * es, d_off + r0 * img_off * es, d_msk + r0 * img_msk * es,
+                                      d_go + r0 * img_out * es, d_gi + r0 * img_in * es, d_goff + r0 * img_off * es,
+                                      d_gmsk + r0 * img_msk * es, n * img_off, n * img_msk, d_ws, ws_chunk, &dc, dtype, g_hc.stream)) return e;
+        GP_CUDA(cudaEventRecord(g_hc.ev_done[c], g_hc.stream));
+        GP_CUDA(cudaStreamWaitEvent(g_hc.s_d2h, g_hc.ev_done[c], 0));
+        GP_CUDA(cudaMemcpyAsync(ro + r0 * img_out * es, d_out + r0 * img_out * es, n * img_out * es, cudaMemcpyDeviceToHost, g_hc.s_d2h));
+        GP_CUDA(cudaMemcpyAsync(rgi + r0 * img_in * es, d_gi + r0 * img_in * es, n * img_in * es, cudaMemcpyDeviceToHost, g_hc.s_d2h));
+        GP_CUDA(cudaMemcpyAsync(rgo + r0 * img_off * es, d_goff + r0 * img_off * es, n * img_off * es, cudaMemcpyDeviceToHost, g_hc.s_d2h));
+        GP_CUDA(cudaMemcpyAsync(rgm + r0 * img_msk * es, d_gmsk + r0 * img_msk * es, n * img_msk * es, cudaMemcpyDeviceToHost, g_hc.s_d2h));
+    }
+    // rows beyond the flat prefix are zero by contract (dcnv3_cuda.cu:131-133): host-side fill, nothing to transfer
+    if (offset_elems > n_off) memset(rgo + n_off * es, 0, (offset_elems - n_off) * es);
+    if (mask_elems > n_msk) memset(rgm + n_msk * es, 0, (mask_elems - n_msk) * es);
+    GP_CUDA(cudaStreamSynchronize(g_hc.s_d2h));
     return GP_OK;
 }
 

@@ -114,6 +114,14 @@ int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void
                            void *h_grad_mask, size_t offset_elems, size_t mask_elems,
                            const gp_dcnv3_desc *desc, int dtype, int device);
 
+/* One training-style call on host buffers: forward + backward of the same inputs, uploaded ONCE, pipelined over `chunks`
+ * RoI chunks (1..64) so that H2D of chunk c+1, the kernels of chunk c and D2H of chunk c-1 overlap.  RoI chunks are exact:
+ * the flat offset/mask addressing is linear in the RoI index.  Synchronous; pinned host memory is needed for overlap. */
+int gp_dcnv3_forward_backward_host(const void *h_input, const void *h_offset, const void *h_mask,
+                                   const void *h_grad_out, void *h_out, void *h_grad_input, void *h_grad_offset,
+                                   void *h_grad_mask, size_t offset_elems, size_t mask_elems,
+                                   const gp_dcnv3_desc *desc, int dtype, int device, int chunks);
+
 /* releases the device scratch cached by the *_host entry points */
 int gp_host_cache_release(void);
 

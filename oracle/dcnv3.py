@@ -116,6 +116,23 @@ def index(offset, N, H, W, kh, kw, sh, sw, ph, pw, dh, dw, group, offset_scale, 
     return hw, flags
 
 
+class CoreFunction(torch.autograd.Function):
+    """Autograd wrapper around the C oracle (forward :216-282, backward :386-487 of dcnv3_im2col_cuda.cuh): the CPU twin of
+    the reference's ``DCNv3Function`` (functions/dcnv3_func.py:22-77), same flat offset / mask addressing."""
+
+    @staticmethod
+    def forward(ctx, input, offset, mask, geom, remove_center):
+        ctx.geom, ctx.rc = geom, remove_center
+        ctx.save_for_backward(input, offset, mask)
+        return forward(input, offset, mask, *geom, remove_center)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        input, offset, mask = ctx.saved_tensors
+        gi, go, gm = backward(input, offset, mask, grad_output.contiguous(), *ctx.geom, ctx.rc)
+        return gi, go, gm, None, None
+
+
 def flat_slice(t: torch.Tensor, N: int, Ho: int, Wo: int) -> torch.Tensor:
     """The stride-2 adapter of SURVEY.md section 0.1: the CUDA kernel reads ``offset``/``mask`` as a flat
     ``[N*Ho*Wo, G*P*(2)]`` matrix (``dcnv3_im2col_cuda.cuh:229,243-244``), i.e. only the first

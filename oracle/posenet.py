@@ -56,7 +56,7 @@ class _LNChannelsLast(nn.Sequential):
 
 
 class DCNv3(nn.Module):
-    differentiable = False   # True: core = dcnv3_core_torch (grid_sample, autograd) on the flat-sliced offset / mask
+    differentiable = False   # True: core = C oracle forward + backward behind autograd (CoreFunction)
 
     def __init__(self, channels, kernel_size=3, stride=1, pad=1, dilation=1, group=4, offset_scale=1.0):
         super().__init__()
@@ -78,9 +78,8 @@ class DCNv3(nn.Module):
         mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(xp.dtype)
         k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
         if self.differentiable:
-            Ho, Wo = core.out_size(H, k, s, p, d), core.out_size(W, k, s, p, d)
-            y = core.dcnv3_core_torch(xp, core.flat_slice(offset.contiguous(), N, Ho, Wo), core.flat_slice(mask.contiguous(), N, Ho, Wo),
-                                      k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale, 0)
+            y = core.CoreFunction.apply(xp.contiguous(), offset.contiguous(), mask.contiguous(),
+                                        (k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale), 0)
         else:
             y = core.forward(xp.contiguous(), offset.contiguous(), mask.contiguous(), k, k, s, s, p, p, d, d, self.group,
                              self.group_channels, self.offset_scale, 0)

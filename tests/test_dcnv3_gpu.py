@@ -296,4 +296,13 @@ def test_host_buffer_entry_points(ops, O):
                                                m.numel(), ctypes.byref(d), _lib.GP_F32, 0), "bwd_host")
     rgi, rgo, rgm = O.backward(inp, off, m, gout, *args, 0)
     assert _rel(gi, rgi) < 1e-4 and _rel(go, rgo) < 1e-4 and _rel(gm, rgm) < 1e-4
+    # pipelined forward+backward over RoI chunks (stride 2, full-resolution offset tensors: flat addressing is chunk-exact)
+    for chunks, dtype, code, tol in ((3, torch.float32, _lib.GP_F32, 1e-4), (4, torch.bfloat16, _lib.GP_BF16, BF16_TOL), (1, torch.float32, _lib.GP_F32, 1e-4)):
+        hi, ho_, hm, hg = (t.to(dtype).pin_memory() for t in (inp, off, m, gout))
+        o2, gi2, go2, gm2 = (torch.full_like(t, 7).pin_memory() for t in (out.to(dtype), hi, ho_, hm))
+        _lib.check(_lib.lib.gp_dcnv3_forward_backward_host(vp(hi), vp(ho_), vp(hm), vp(hg), vp(o2), vp(gi2), vp(go2), vp(gm2),
+                                                           ho_.numel(), hm.numel(), ctypes.byref(d), code, 0, chunks), "fwd_bwd_host")
+        ro = O.forward(hi.float(), ho_.float(), hm.float(), *args, 0)
+        r1, r2, r3 = O.backward(hi.float(), ho_.float(), hm.float(), hg.float(), *args, 0)
+        assert _rel(o2, ro) < tol and _rel(gi2, r1) < tol and _rel(go2, r2) < tol and _rel(gm2, r3) < tol, (chunks, dtype)
     _lib.lib.gp_host_cache_release()
