@@ -182,7 +182,12 @@ def test_training_path_matches_reference_golden_and_oracle_gradients(OP):
         # 1e-4, tests/test_dcnv3_gpu.py).  End to end the offsets themselves differ by ~1e-6 px between the CPU and GPU forward,
         # which flips floor() for the few samples that sit on an integer boundary; d(out)/d(offset) is discontinuous there, so
         # aggregated gradients upstream of an offset branch agree to ~2e-3 (measured), not 1e-4.
-        assert pg[name].grad is not None and rel(pg[name].grad, po[name].grad) < 1e-2, (name, rel(pg[name].grad, po[name].grad))
+        # Which samples flip depends on the library kernels the box picks, so the bar is the relative L2 error (a flip moves a
+        # few entries) plus a looser max-error bound (measured 2e-3 .. 1.3e-2 across boxes).
+        assert pg[name].grad is not None, name
+        a, b = pg[name].grad.detach().cpu().double(), po[name].grad.double()
+        l2 = ((a - b).norm() / b.norm()).item()
+        assert l2 < 1e-2 and rel(a, b) < 5e-2, (name, l2, rel(a, b))
     assert pg["nocs_encoder.features.0.bn.weight"].grad is None   # built but unused in the reference, too
 
 
