@@ -31,6 +31,54 @@ int gp_dwconv3x3_ln_gelu(const void *x, const float *w_t, const float *bias, con
     return (int)cudaGetLastError();
 }
 
+int gp_small_k_linear(const void *x, const float *w_t, const float *bias, void *out, long long rows, int K, int C, int dtype,
+                      void *stream) {
+    if (!x || !w_t || !bias || !out) return GP_ERR_NULL;
+    if (rows < 0 || C <= 0 || C % 8 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (K != 3) return GP_ERR_UNSUPPORTED;
+    if (!al16(out)) return GP_ERR_ALIGN;
+    if (rows == 0) return GP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = dtype == GP_F32 ? 4 : 8, pstep = 256 / (C / V);
+    if (pstep < 1) return GP_ERR_SHAPE;
+    const long long want = (rows + pstep - 1) / pstep;
+    const unsigned grid = (unsigned)(want < 148ll * 32 ? want : 148ll * 32);
+    switch (dtype) {
+        case GP_F32: small_k_linear_kernel<float, 3><<<grid, 256, 0, st>>>((const float *)x, w_t, bias, (float *)out, rows, C); break;
+        case GP_BF16: small_k_linear_kernel<__nv_bfloat16, 3><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, w_t, bias, (__nv_bfloat16 *)out, rows, C); break;
+        case GP_F16: small_k_linear_kernel<__half, 3><<<grid, 256, 0, st>>>((const __half *)x, w_t, bias, (__half *)out, rows, C); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *bias, const float *ln_w, const float *ln_b,
+                                void *out, int N, int H, int W, int K, int C, long long rows, float eps, int dtype, void *stream) {
+    if (!x || !w_eff || !bias || !ln_w || !ln_b || !out) return GP_ERR_NULL;
+    if (N <= 0 || H <= 0 || W <= 0 || rows < 0 || rows > (long long)N * H * W) return GP_ERR_SHAPE;
+    if (K != 3 || (C != 128 && C != 256 && C != 512)) return GP_ERR_UNSUPPORTED;
+    if (!al16(w_eff) || !al16(bias) || !al16(ln_w) || !al16(ln_b) || !al16(out)) return GP_ERR_ALIGN;
+    if (rows == 0) return GP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int px = (W % 4 == 0 && C <= 256) ? 4 : 1;   // pixels per warp: the composed weights are loaded once per 4 pixels
+    const long long want = (rows + 8 * px - 1) / (8 * px);
+    const unsigned grid = (unsigned)(want < 148ll * 64 ? want : 148ll * 64);
+#define GP_SK(TT, JJ) do { if (px == 4) smallk_dwconv_ln_gelu_kernel<TT, JJ, 3, 4><<<grid, 256, 0, st>>>((const TT *)x, w_eff, bias, ln_w, ln_b, (TT *)out, H, W, rows, eps); \
+                           else smallk_dwconv_ln_gelu_kernel<TT, JJ, 3, 1><<<grid, 256, 0, st>>>((const TT *)x, w_eff, bias, ln_w, ln_b, (TT *)out, H, W, rows, eps); } while (0)
+#define GP_SK_T(TT) do { if (C == 128) GP_SK(TT, 1); else if (C == 256) GP_SK(TT, 2); else smallk_dwconv_ln_gelu_kernel<TT, 4, 3, 1><<<grid, 256, 0, st>>>((const TT *)x, w_eff, bias, ln_w, ln_b, (TT *)out, H, W, rows, eps); } while (0)
+    switch (dtype) {
+        case GP_F32: GP_SK_T(float); break;
+        case GP_BF16: GP_SK_T(__nv_bfloat16); break;
+        case GP_F16: GP_SK_T(__half); break;
+        default: return GP_ERR_DTYPE;
+    }
+#undef GP_SK_T
+#undef GP_SK
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 // slab decomposition shared by the channel-last elementwise kernels: grid (slabs, N), >= 32 pixels per CTA
 static dim3 slab_grid(int N, int npix, int ctas_per_sm, int *ppc) {
     int slabs = (int)((148ll * ctas_per_sm + N - 1) / N);
@@ -45,6 +93,7 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, c
     if (!x || !y || !stats || !gamma || !beta) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || C % G || (C / G) % 4 || C / 4 > 256) return GP_ERR_SHAPE;
     if (act < 0 || act > 2) return GP_ERR_UNSUPPORTED;
+    if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t ce = cudaMemsetAsync(stats, 0, (size_t)N * G * 2 * sizeof(float), st);
@@ -68,9 +117,39 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, c
     return (int)cudaGetLastError();
 }
 
+int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, const float *gamma, const float *beta, const float *w,
+                             const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC, int dtype,
+                             void *stream) {
+    if (!x || !y || !stats || !gamma || !beta || !w || !bias) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || G <= 0 || C % G || (C / G) % 4) return GP_ERR_SHAPE;
+    if (C != 256 || OC != 3 || act < 0 || act > 2) return GP_ERR_UNSUPPORTED;   // the decoder's out_layer
+    if (!al16(x) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t ce = cudaMemsetAsync(stats, 0, (size_t)N * G * 2 * sizeof(float), st);
+    if (ce != cudaSuccess) return (int)ce;
+    const int HW = H * W;
+    int ppc = 0, appc = 0;
+    const dim3 sgrid = slab_grid(N, HW, 8, &ppc), agrid = slab_grid(N, HW, 8, &appc);
+#define GP_GNC_APPLY(TT, AA) gn_act_conv1x1_kernel<TT, AA, 8, 3><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, w, bias, (TT *)y, HW, G, eps, appc)
+#define GP_GNC(TT) do { gn_stats_kernel<TT><<<sgrid, 256, 2 * G * sizeof(float), st>>>((const TT *)x, stats, HW, C, G, ppc); \
+                        if (act == ACT_RELU) GP_GNC_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GNC_APPLY(TT, ACT_GELU); \
+                        else GP_GNC_APPLY(TT, ACT_NONE); } while (0)
+    switch (dtype) {
+        case GP_F32: GP_GNC(float); break;
+        case GP_BF16: GP_GNC(__nv_bfloat16); break;
+        case GP_F16: GP_GNC(__half); break;
+        default: return GP_ERR_DTYPE;
+    }
+#undef GP_GNC
+#undef GP_GNC_APPLY
+    count_launch(2);
+    return (int)cudaGetLastError();
+}
+
 int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream) {
     if (!x || !y) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || C % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y)) return GP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     int ppc = 0;
@@ -85,9 +164,28 @@ int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, i
     return (int)cudaGetLastError();
 }
 
+int gp_stem_s2d_pack(const float *img, void *out, int N, int H, int W, int dtype, void *stream) {
+    if (!img || !out) return GP_ERR_NULL;
+    if (N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2) return GP_ERR_SHAPE;
+    if (!al16(out) || (reinterpret_cast<uintptr_t>(img) & 7u)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)N * (H / 2 + 3) * (W / 2 + 3);
+    const long long want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148ll * 32 ? want : 148ll * 32);
+    switch (dtype) {
+        case GP_F32: stem_s2d_pack_kernel<float><<<grid, 256, 0, st>>>(img, (float *)out, N, H, W); break;
+        case GP_BF16: stem_s2d_pack_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(img, (__nv_bfloat16 *)out, N, H, W); break;
+        case GP_F16: stem_s2d_pack_kernel<__half><<<grid, 256, 0, st>>>(img, (__half *)out, N, H, W); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream) {
     if (!x || !y) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || C % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y)) return GP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
     const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;

@@ -51,6 +51,41 @@ def dwconv3x3_ln_gelu(x, w_t, bias, ln_w, ln_b, rows=None, eps=1e-6):
     return out
 
 
+def small_k_linear(x, w_t, bias):
+    """``x (..., K) @ w_t (K, C) + bias`` for K = 3 input channels (the composed ``input_proj(conv1x1(x))`` of the first
+    MAPEncoder layer); returns ``(..., C)`` in ``x.dtype``."""
+    _need_cuda("input", x)
+    _need_cuda("weight", w_t, torch.float32)
+    _need_cuda("bias", bias, torch.float32)
+    dt = _DTYPES.get(x.dtype)
+    K, C = w_t.shape
+    if dt is None or x.shape[-1] != K or bias.shape != (C,):
+        raise RuntimeError(f"small_k_linear: unsupported input {x.dtype} {tuple(x.shape)} / weight {tuple(w_t.shape)}")
+    out = torch.empty((*x.shape[:-1], C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_small_k_linear(_vp(x), _vp(w_t), _vp(bias), _vp(out), x.numel() // K, K, C, dt, _stream(x)), "small_k_linear")
+    return out
+
+
+def smallk_dwconv3x3_ln_gelu(x, w_eff, bias, ln_w, ln_b, rows=None, eps=1e-6):
+    """``GELU(LayerNorm(DWConv3x3(Conv1x1_{K->C}(x))))`` for the first ``rows`` pixels of channel-last ``x`` (N,H,W,K), K = 3,
+    without materialising the C-channel convolution output.  ``w_eff`` (9, K+1, C) fp32, see ``include/givepose_b200.h``."""
+    _need_cuda("input", x)
+    for n, t in (("w_eff", w_eff), ("dw bias", bias), ("ln weight", ln_w), ("ln bias", ln_b)):
+        _need_cuda(n, t, torch.float32)
+    dt = _DTYPES.get(x.dtype)
+    if dt is None or x.dim() != 4 or w_eff.dim() != 3 or w_eff.shape[1] != x.shape[-1] + 1:
+        raise RuntimeError(f"smallk_dwconv3x3_ln_gelu: unsupported input {x.dtype} {tuple(x.shape)}")
+    N, H, W, K = x.shape
+    C = w_eff.shape[-1]
+    rows = N * H * W if rows is None else int(rows)
+    out = torch.empty((rows, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_smallk_dwconv3x3_ln_gelu(_vp(x), _vp(w_eff), _vp(bias), _vp(ln_w), _vp(ln_b), _vp(out), N, H, W, K, C, rows,
+                                              float(eps), dt, _stream(x)), "smallk_dwconv3x3_ln_gelu")
+    return out
+
+
 def _nhwc(name, x):
     _need_cuda(name, x)
     dt = _DTYPES.get(x.dtype)
@@ -72,6 +107,38 @@ def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=Fa
         check(lib.gp_groupnorm_act(_vp(x), _vp(y), _vp(stats), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
                                    ACT[act], dt, _stream(x)), "groupnorm_act")
     return upsample_bilinear2x(y) if upsample2x else y
+
+
+def groupnorm_act_conv1x1(x, gamma, beta, weight, bias, groups=32, eps=1e-5, act="gelu"):
+    """``Conv1x1(act(GroupNorm(x))) + bias`` on channel-last ``x`` (N,H,W,256) -> (N,H,W,3): the decoder's last GN/GELU
+    fused with its ``out_layer`` (``xyz_head.py:349-366``).  ``weight`` (3,256) / ``bias`` (3,) / ``gamma`` / ``beta`` fp32."""
+    dt = _nhwc("input", x)
+    for n, t in (("gn weight", gamma), ("gn bias", beta), ("out_layer weight", weight), ("out_layer bias", bias)):
+        _need_cuda(n, t, torch.float32)
+    N, H, W, C = x.shape
+    OC = weight.shape[0]
+    if weight.shape != (OC, C) or bias.shape != (OC,):
+        raise RuntimeError("groupnorm_act_conv1x1: inconsistent weight / bias shapes")
+    y = torch.empty((N, H, W, OC), dtype=x.dtype, device=x.device)
+    stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_groupnorm_act_conv1x1(_vp(x), _vp(y), _vp(stats), _vp(gamma), _vp(beta), _vp(weight), _vp(bias), N, H, W, C,
+                                           int(groups), float(eps), ACT[act], OC, dt, _stream(x)), "groupnorm_act_conv1x1")
+    return y
+
+
+def stem_s2d_pack(img, dtype):
+    """fp32 NCHW RoI crops (N,3,H,W) -> (N, H/2+3, W/2+3, 16) channel-last ``dtype``: the 2x2 space-to-depth operand of a
+    7x7/2 stem convolution run as a 4x4/1 convolution (see ``posenet._stem``)."""
+    _need_cuda("roi_img", img, torch.float32)
+    dt = _DTYPES.get(dtype)
+    if dt is None or img.dim() != 4 or img.shape[1] != 3 or img.shape[2] % 2 or img.shape[3] % 2:
+        raise RuntimeError(f"stem_s2d_pack: unsupported input {dtype} {tuple(img.shape)}")
+    N, _, H, W = img.shape
+    out = torch.empty((N, H // 2 + 3, W // 2 + 3, 16), dtype=dtype, device=img.device)
+    with torch.cuda.device(img.device):
+        check(lib.gp_stem_s2d_pack(_vp(img), _vp(out), N, H, W, dt, _stream(img)), "stem_s2d_pack")
+    return out
 
 
 def upsample_bilinear2x(x):

@@ -52,6 +52,8 @@ class PoseNetConfig:
     dataset: str = "Real"         # 'wild6d' rescales z by fx/590 (pose_from_pred_centroid_z.py:110-111)
     precision: str = "fp32"       # 'fp32' (TF32 off, parity mode) | 'bf16'
     rot_on_cpu: bool = True       # reference behaviour at test time
+    h2d_chunk_rois: int = 256     # host inputs: RoI crops are uploaded in chunks of this many RoIs on a copy stream while the
+                                  # backbone runs on the previous chunk (0 = one blocking upload like the reference)
 
 
 def _fused(x: torch.Tensor) -> bool:
@@ -151,28 +153,68 @@ class DCNv3(nn.Module):
                            "ln_w": ln.weight.detach().float().contiguous(), "ln_b": ln.bias.detach().float().contiguous()}
         return self._cache
 
+    def _fusable(self, x, C):
+        return (_fused(x) and self.dw_kernel_size == 3 and C in (128, 256, 512) and x.is_cuda
+                and x.dtype in (torch.float32, torch.bfloat16, torch.float16))
+
+    def _geom(self):
+        k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
+        return (k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale)
+
+    def _sample(self, x, x1):
+        """offset / mask-logit Linears on the computed rows, fused-softmax sampler, output projection."""
+        offset = _lin(x1, self.offset)
+        logits = _lin(x1, self.mask)
+        x = dcnv3_forward(x.contiguous(), offset.contiguous(), logits.contiguous(), *self._geom(), 256, self.remove_center,
+                          mask_is_logits=True)
+        return _lin(x, self.output_proj)
+
+    def _composed_params(self, conv):
+        """``conv`` (1x1, K -> C) feeds this module and both of its consumers are linear in its output: compose
+        ``input_proj o conv`` and ``dw_conv o conv`` (fp64 products, stored fp32); see ``include/givepose_b200.h``."""
+        dw, ln = self.dw_conv[0], self.dw_conv[1][1]
+        ps = (conv.weight, conv.bias, self.input_proj.weight, self.input_proj.bias, dw.weight, dw.bias, ln.weight, ln.bias)
+        key = (conv.weight.device,) + tuple(p._version for p in ps)
+        if self._cache.get("ckey") != key:
+            with torch.no_grad():
+                Wc, bc = conv.weight.detach().double().flatten(1), conv.bias.detach().double()            # (C,K), (C,)
+                Wip, bip = self.input_proj.weight.detach().double(), self.input_proj.bias.detach().double()
+                wdw = dw.weight.detach().double().reshape(self.channels, 9)                              # (C, 9), tap = ky*3+kx
+                w_eff = torch.cat([wdw.t()[:, None, :] * Wc.t()[None, :, :], (wdw * bc[:, None]).t()[:, None, :]], dim=1)
+                self._cache.update({"ckey": key, "wp_t": (Wip @ Wc).t().float().contiguous(), "bp": (Wip @ bc + bip).float().contiguous(),
+                                    "w_eff": w_eff.float().contiguous(), "dw_b": dw.bias.detach().float().contiguous(),
+                                    "cln_w": ln.weight.detach().float().contiguous(), "cln_b": ln.bias.detach().float().contiguous()})
+        return self._cache
+
+    def forward_after_conv1x1(self, x_small, conv):
+        """``self(conv(x_small))`` for a 1x1 ``conv`` with K = 3 input channels (first MAPEncoder layer) without writing the
+        C-channel convolution output."""
+        N, H, W, K = x_small.shape
+        if not (K == 3 and conv.bias is not None and self._fusable(x_small, self.channels)):
+            return self(_conv1x1_rows(x_small, conv))
+        Ho, Wo = self._out_hw(H, W)
+        rows = min(N * Ho * Wo, N * H * W)
+        c = self._composed_params(conv)
+        x_small = x_small.contiguous()
+        x = ops.small_k_linear(x_small, c["wp_t"], c["bp"])
+        x1 = ops.smallk_dwconv3x3_ln_gelu(x_small, c["w_eff"], c["dw_b"], c["cln_w"], c["cln_b"], rows, eps=1e-6)
+        return self._sample(x, x1)
+
     def forward(self, input):
         N, H, W, C = input.shape
-        k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
-        geom = (k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale)
-        x = _lin(input, self.input_proj)
-        fusable = (_fused(input) and self.dw_kernel_size == 3 and C in (128, 256, 512) and input.is_cuda
-                   and input.dtype in (torch.float32, torch.bfloat16, torch.float16))
-        if fusable:
+        geom = self._geom()
+        if self._fusable(input, C):
             # the sampler reads offset / mask through their flat [N*Ho*Wo]-row prefix (cuh:229,243-244): compute only those rows
             Ho, Wo = self._out_hw(H, W)
             rows = min(N * Ho * Wo, N * H * W)
             c = self._dw_params(input.device)
             x1 = ops.dwconv3x3_ln_gelu(input.contiguous(), c["w_t"], c["b"], c["ln_w"], c["ln_b"], rows, eps=1e-6)
-            offset = _lin(x1, self.offset)
-            logits = _lin(x1, self.mask)
-            x = dcnv3_forward(x.contiguous(), offset.contiguous(), logits.contiguous(), *geom, 256, self.remove_center,
-                              mask_is_logits=True)
-        else:
-            x1 = self.dw_conv(input.permute(0, 3, 1, 2))
-            offset = self.offset(x1)
-            mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(x.dtype)
-            x = DCNv3Function.apply(x.contiguous(), offset.contiguous(), mask.contiguous(), *geom, 256, self.remove_center)
+            return self._sample(_lin(input, self.input_proj), x1)
+        x = _lin(input, self.input_proj)
+        x1 = self.dw_conv(input.permute(0, 3, 1, 2))
+        offset = self.offset(x1)
+        mask = F.softmax(self.mask(x1).reshape(N, H, W, self.group, -1), -1).reshape(N, H, W, -1).type(x.dtype)
+        x = DCNv3Function.apply(x.contiguous(), offset.contiguous(), mask.contiguous(), *geom, 256, self.remove_center)
         return _lin(x, self.output_proj)
 
 
@@ -188,6 +230,8 @@ class DCNv3_C(nn.Module):
         self.gelu = nn.GELU()
 
     def forward_nhwc(self, x):
+        if x.shape[-1] == 3 and _fused(x):
+            return self.dcnv3.forward_after_conv1x1(x, self.conv)
         return self.dcnv3(_conv1x1_rows(x, self.conv))
 
     def forward(self, x):
@@ -298,6 +342,13 @@ class TopDownXyzHead(nn.Module):
         x = fs[6].forward_nhwc(x)
         x = fs[7].forward_nhwc(x, upsample2x=True)     # features.8
         x = fs[9].forward_nhwc(x)
+        if _fused(x) and x.shape[-1] == 256 and self.out_layer.out_channels == 3:
+            # last ConvModule: conv -> [GN -> GELU -> out_layer 1x1] in one pass; the 256-channel activation is never written
+            last = fs[10]
+            return ops.groupnorm_act_conv1x1(_conv_nhwc(x, last.conv).contiguous(), _cached(last.norm.weight, torch.float32),
+                                             _cached(last.norm.bias, torch.float32),
+                                             _cached(self.out_layer.weight, torch.float32, lambda w: w.flatten(1), "rows"),
+                                             _cached(self.out_layer.bias, torch.float32), last.norm.num_groups, last.norm.eps, "gelu")
         x = fs[10].forward_nhwc(x)
         return _conv1x1_rows(x, self.out_layer)
 
@@ -336,7 +387,16 @@ class ConvPnPNet(nn.Module):
 
     def forward_nhwc(self, x):
         for i in range(0, 9, 3):
-            x = _gn_act_nhwc(_conv_nhwc(x, self.features[i]), self.features[i + 1], "relu")
+            conv = self.features[i]
+            if i == 0 and _fused(x) and x.shape[-1] % 8:
+                # 5 input channels (3 IVFC + 2 image coordinates) send cuDNN to a SIMT kernel: zero-pad activation and weight
+                # to 8 channels (exact) so the stride-2 3x3 runs as a tensor-core implicit GEMM
+                pad = 8 - x.shape[-1] % 8
+                w = _cached(conv.weight, x.dtype, lambda t: F.pad(t, (0, 0, 0, 0, 0, pad)), "cin8")
+                y = F.conv2d(F.pad(x, (0, pad)).permute(0, 3, 1, 2), w, None, conv.stride, conv.padding).permute(0, 2, 3, 1)
+            else:
+                y = _conv_nhwc(x, conv)
+            x = _gn_act_nhwc(y, self.features[i + 1], "relu")
         pnp_feat = x.permute(0, 3, 1, 2)
         flat = pnp_feat.reshape(x.shape[0], -1)   # NCHW flatten order (conv_pnp_net.py:168-170): checkpoint compatible
         # fc1 || fc1_z read the same 8192-wide activation: one GEMM over the concatenated weights
@@ -446,6 +506,38 @@ def _conv_bn_act(x, conv, bn, relu=True, residual=None):
 _conv_bn_act.fused_ok = True
 
 
+def _stem_s2d(img, conv, bn, dtype):
+    """7x7/2 stem over the fp32 NCHW RoI crops as a 4x4/1 convolution over the 2x2 space-to-depth image (12 -> 16 channels,
+    K = 256): cuDNN's 3-channel 7x7 kernels take 10.6 ms per 1024 RoIs on B200, this form 2.6 ms.  ``ops.stem_s2d_pack`` reads
+    the crops once (it replaces the dtype cast and the channels_last copy); the weight is the folded 7x7 kernel padded to
+    8x8 with a zero tap in front and regrouped the same way.  Same sums as the direct convolution, different order."""
+    vers = (conv.weight._version, bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, dtype,
+            conv.weight.device)
+    hit = getattr(conv, "_gp_fold_s2d", None)
+    if hit is None or hit[0] != vers:
+        with torch.no_grad():
+            scale = bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)
+            w = conv.weight.float() * scale.view(-1, 1, 1, 1)                             # (O, 3, 7, 7)
+            O = w.shape[0]
+            w = F.pad(w, (1, 0, 1, 0)).reshape(O, 3, 4, 2, 4, 2).permute(0, 1, 3, 5, 2, 4)   # o, c, ry, rx, a, b
+            w = F.pad(w.reshape(O, 12, 4, 4), (0, 0, 0, 0, 0, 4)).to(dtype).contiguous(memory_format=torch.channels_last)
+            b = (bn.bias.float() - bn.running_mean.float() * scale).to(dtype).contiguous()
+        hit = (vers, w, b)
+        conv._gp_fold_s2d = hit
+    _, w, b = hit
+    x = ops.stem_s2d_pack(img, dtype).permute(0, 3, 1, 2)
+    if hasattr(torch, "cudnn_convolution_relu") and _conv_bn_act.fused_ok:
+        try:
+            y = torch.cudnn_convolution_relu(x, w, b, (1, 1), (0, 0), (1, 1), 1)
+        except RuntimeError:
+            _conv_bn_act.fused_ok = False
+            y = F.conv2d(x, w, b)
+    else:
+        y = F.conv2d(x, w, b)
+    y = ops.maxpool3x3s2(y.permute(0, 2, 3, 1).contiguous(), relu=True)
+    return y.permute(0, 3, 1, 2)
+
+
 def _stem(x, conv, bn):
     """7x7/2 stem conv + folded BN, then ReLU + 3x3/2 max-pool in one channel-last kernel (ReLU commutes with max)."""
     w, b = _folded(conv, bn, x.dtype)
@@ -459,11 +551,19 @@ class ResNet34Backbone(nn.Module):
         super().__init__()
         self.trunk, self.neck = ResNet34Trunk(), nn.Conv2d(512, out_channels, 1)
 
-    def forward(self, x):
+    def forward(self, x, compute_dtype=None):
+        """``x``: RoI crops (B,3,H,W).  At inference ``compute_dtype`` (default: ``x.dtype``) selects the activation type; fp32
+        NCHW crops go through the packed space-to-depth stem, so the caller need not cast / re-layout them first."""
         if self.training or torch.is_grad_enabled():
             return [self.neck(self.trunk(x))]
         t = self.trunk   # inference: BN folded, ReLU / residual add in the convolution epilogue
-        x = _stem(x, t.conv1, t.bn1)
+        dtype = compute_dtype or x.dtype
+        c1 = t.conv1
+        if (x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 3 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0
+                and c1.kernel_size == (7, 7) and c1.stride == (2, 2) and c1.padding == (3, 3)):
+            x = _stem_s2d(x, c1, t.bn1, dtype)
+        else:
+            x = _stem(x.to(dtype).contiguous(memory_format=torch.channels_last), c1, t.bn1)
         for layer in (t.layer1, t.layer2, t.layer3, t.layer4):
             for blk in layer:
                 idt = x if blk.downsample is None else _conv_bn_act(x, blk.downsample[0], blk.downsample[1], relu=False)
@@ -508,19 +608,76 @@ class PoseNet(nn.Module):
         finally:
             torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
+    def _backbone_pipelined(self, img_h, late, dev, dtype):
+        """Host-resident RoI crops (the reference uploads them inside ``forward`` too, PoseNet.py:174): chunks of
+        ``cfg.h2d_chunk_rois`` RoIs go up on a copy stream while the backbone -- per-RoI independent, unlike the DCNv3
+        encoder with its batch-coupled offset rows -- runs on the previous chunk.  ``late`` (mask, 2-D
+        coordinates: read only after the heads) follows on the same copy stream; returns the features and
+        ``{name: (device tensor, event to wait for)}``."""
+        main = torch.cuda.current_stream(dev)
+        side = getattr(self, "_copy_stream", None)
+        if side is None or side.device != dev:
+            side = self._copy_stream = torch.cuda.Stream(dev)
+        B, chunk = img_h.shape[0], self.cfg.h2d_chunk_rois
+        img_d = torch.empty(img_h.shape, dtype=img_h.dtype, device=dev)
+        late_d = {k: torch.empty(v.shape, dtype=v.dtype, device=dev) for k, v in late.items()}
+        side.wait_stream(main)   # the buffers above belong to `main`'s allocation order
+        events, late_out = [], {}
+        with torch.cuda.stream(side):
+            for c0 in range(0, B, chunk):
+                img_d[c0:c0 + chunk].copy_(img_h[c0:c0 + chunk], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                events.append(ev)
+            for k, v in late.items():
+                late_d[k].copy_(v, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(side)
+                late_out[k] = (late_d[k], ev)
+        feats = []
+        for i, c0 in enumerate(range(0, B, chunk)):
+            main.wait_event(events[i])
+            feats.append(self.backbone(img_d[c0:c0 + chunk], dtype)[0])
+        return [torch.cat(feats)], late_out
+
     def forward(self, data, device, do_loss=False, pred_scale=None):
         dev = torch.device(device)
         if dev.type != "cuda":
             raise RuntimeError("givepose_b200.PoseNet: Not implemented on the CPU (there is no CPU fallback)")
-        img = data["roi_img"].to(dev, non_blocking=True)
-        mask = data["roi_mask_deform" if do_loss else "roi_mask"].to(dev, non_blocking=True)
-        # Resize(out_res, NEAREST) of the square mask: src index = floor(dst * in/out) (PoseNet.py:170,180)
-        step = mask.shape[-1] // self.out_res
-        mask_out = mask[..., ::step, ::step] if mask.shape[-1] % self.out_res == 0 else F.interpolate(mask, size=self.out_res, mode="nearest")
-        if self.cfg.precision == "bf16" and not torch.is_grad_enabled():
-            img = img.to(torch.bfloat16)
+        if dev.index is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        img, mask = data["roi_img"], data["roi_mask_deform" if do_loss else "roi_mask"]
+        fast_backbone = isinstance(self.backbone, ResNet34Backbone) and not torch.is_grad_enabled()
+        cdtype = torch.bfloat16 if self.cfg.precision == "bf16" else torch.float32
+        feat, coord2d, late = None, data["roi_coord_2d"], {}
+        if (fast_backbone and not img.is_cuda and img.is_pinned() and not mask.is_cuda and mask.is_pinned()
+                and 0 < self.cfg.h2d_chunk_rois < img.shape[0] and img.dtype == torch.float32):
+            with self._precision():
+                host_late = {"mask": mask}
+                if not coord2d.is_cuda and coord2d.is_pinned():
+                    host_late["coord2d"] = coord2d
+                feat, late = self._backbone_pipelined(img, host_late, dev, cdtype)
+        else:
+            img = img.to(dev, non_blocking=True)
+            mask = mask.to(dev, non_blocking=True)
+
+        def arrived(name, fallback):   # a tensor uploaded on the copy stream: wait for it right before its first use
+            if name not in late:
+                return fallback.to(dev, non_blocking=True)
+            t, ev = late[name]
+            torch.cuda.current_stream(dev).wait_event(ev)
+            return t
+
         with self._precision():
-            feat = self.backbone(img.contiguous(memory_format=torch.channels_last))
+            if feat is not None:
+                pass
+            elif fast_backbone:
+                # fp32 NCHW crops straight into the packed stem: no separate cast / channels_last copies
+                feat = self.backbone(img.float().contiguous(), cdtype)
+            else:
+                if self.cfg.precision == "bf16" and not torch.is_grad_enabled():
+                    img = img.to(torch.bfloat16)
+                feat = self.backbone(img.contiguous(memory_format=torch.channels_last))
             f_nhwc = feat[0].permute(0, 2, 3, 1)                              # (B, 8, 8, 1024) channel-last view
             if not f_nhwc.is_contiguous():
                 f_nhwc = f_nhwc.contiguous()
@@ -529,8 +686,12 @@ class PoseNet(nn.Module):
             nocs_feat = self.nocs_encoder.forward_nhwc(nocs)                  # (B, 8, 8, 256)
             conv_feat256 = _conv1x1_rows(f_nhwc, self.feat_reducer)
             ivfc = self.xyz_deform_head.forward_nhwc(torch.cat([conv_feat256, nocs_feat.to(conv_feat256.dtype)], dim=-1))
-            coord2d = data["roi_coord_2d"].to(dev, non_blocking=True).permute(0, 2, 3, 1)
+            coord2d = arrived("coord2d", coord2d).permute(0, 2, 3, 1)
             rot6, t, _ = self.pnp_net.forward_nhwc(torch.cat([ivfc, coord2d.to(ivfc.dtype)], dim=-1))
+        mask = arrived("mask", mask)
+        # Resize(out_res, NEAREST) of the square mask: src index = floor(dst * in/out) (PoseNet.py:170,180)
+        step = mask.shape[-1] // self.out_res
+        mask_out = mask[..., ::step, ::step] if mask.shape[-1] % self.out_res == 0 else F.interpolate(mask, size=self.out_res, mode="nearest")
         coor_xyz_nocs = nocs.float().permute(0, 3, 1, 2)
         coor_xyz_ivfc = ivfc.float().permute(0, 3, 1, 2)
         mean_size = data["mean_size"].to(dev)

@@ -134,10 +134,39 @@ int gp_host_cache_release(void);
 int gp_dwconv3x3_ln_gelu(const void *x, const float *w_t, const float *bias, const float *ln_w, const float *ln_b,
                          void *out, int N, int H, int W, int C, long long rows, float eps, int dtype, void *stream);
 
+/* First MAPEncoder layer (conv_pnp_net.py:259-272, network/dcnv3.py:32-38): DCNv3_C's 1x1 convolution lifts the K = 3
+ * coordinate channels to C, and both consumers are linear in its output, so that C-channel tensor is never written:
+ *   gp_small_k_linear             out(rows,C) = x(rows,K) . w_t[K][C] + bias     (w_t = (W_ip W_c)^T, bias = W_ip b_c + b_ip:
+ *                                 input_proj(conv(x)), modules/dcnv3.py:325, composed by the caller in fp32)
+ *   gp_smallk_dwconv3x3_ln_gelu   GELU(LN(DWConv3x3(conv(x)))) for the first `rows` pixels of x (N,H,W,K);
+ *                                 w_eff[9][K+1][C]: w_eff[t][k][c] = w_dw[c,t] W_c[c,k], w_eff[t][K][c] = w_dw[c,t] b_c[c]
+ *                                 (the conv bias enters only through taps inside the image: zero padding applies to conv(x)).
+ * Supported: K == 3. */
+int gp_small_k_linear(const void *x, const float *w_t, const float *bias, void *out, long long rows, int K, int C, int dtype,
+                      void *stream);
+int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *bias, const float *ln_w, const float *ln_b,
+                                void *out, int N, int H, int W, int K, int C, long long rows, float eps, int dtype, void *stream);
+
 /* y = act(GroupNorm_G(x)) on channel-last (N,H,W,C) activations (layer_utils.py:32-60 "GN", conv_module.py order
  * conv -> norm -> act); act: 0 none, 1 ReLU, 2 exact GELU.  stats: N*G*2 floats of scratch (zeroed by the call). */
 int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, const float *beta, int N, int H, int W,
                      int C, int G, float eps, int act, int dtype, void *stream);
+
+/* y = Conv1x1_{C->OC}(act(GroupNorm_G(x))) + bias: the decoder's last ConvModule norm/activation fused with its
+ * out_layer (xyz_head.py:349-366, Conv1x1 256 -> 3); the normalised C-channel activation is never written.
+ * x (N,H,W,C) channel-last, y (N,H,W,OC) of `dtype`; w [OC][C] and bias [OC] fp32.  Supported: C == 256, OC == 3.
+ * For 16-bit storage GELU is evaluated with a tanh-form fit of the erf GELU (error < 2.5e-4 |x|, below the bf16
+ * rounding of the result); fp32 keeps the erf form (abs error 1.5e-7).  The same holds for gp_groupnorm_act. */
+int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, const float *gamma, const float *beta, const float *w,
+                             const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC, int dtype,
+                             void *stream);
+
+/* Operand packing for a 7x7 / stride-2 / pad-3 stem convolution over 3 input channels (network/resnet.py:104, the
+ * stand-in backbone of the synthetic runs) evaluated as a 4x4 / stride-1 convolution over the 2x2 space-to-depth image:
+ * img fp32 (N,3,H,W) NCHW  ->  out (N, H/2+3, W/2+3, 16) channel-last of `dtype`,
+ * out[n, 2+y2, 2+x2, c*4 + ry*2 + rx] = img[n, c, 2*y2+ry, 2*x2+rx], zero elsewhere (spatial padding 2 before / 1 after,
+ * channels 12..15). */
+int gp_stem_s2d_pack(const float *img, void *out, int N, int H, int W, int dtype, void *stream);
 
 /* nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) of TopDownXyzHead (xyz_head.py:262-265) on channel-last
  * activations: (N,H,W,C) -> (N,2H,2W,C). */

@@ -70,6 +70,65 @@ def test_groupnorm_act_matches_torch(act, up, shape):
     assert rel(got, y.permute(0, 2, 3, 1)) < 5e-6
 
 
+@pytest.mark.parametrize("act", ["relu", "gelu"])
+@pytest.mark.parametrize("shape", [(3, 16, 16, 256), (2, 8, 8, 128), (1, 5, 7, 256)])
+def test_groupnorm_act_bf16_within_storage_rounding(act, shape):
+    """16-bit storage: GELU goes through the tanh-form fit of the erf GELU (error < 2.5e-4 |x|); the bar is the bf16 rounding
+    of the stored result (2^-8 relative), checked per element against torch's exact GELU on the same bf16-rounded input."""
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    x = (torch.randn(*shape, generator=g) * 2 + 0.5).bfloat16()
+    C = shape[-1]
+    gam, bet = torch.rand(C, generator=g) + 0.5, torch.randn(C, generator=g) * 0.1
+    y = F.group_norm(x.float().permute(0, 3, 1, 2), 32, gam, bet, 1e-5)
+    y = (F.relu(y) if act == "relu" else F.gelu(y)).permute(0, 2, 3, 1)
+    got = ops.groupnorm_act(x.cuda(), gam.cuda(), bet.cuda(), 32, 1e-5, act).float().cpu()
+    assert got.dtype == torch.float32 and ((got - y).abs() <= 2.0 ** -8 * y.abs() + 1.5e-3).all()
+    assert rel(got, y) < 4e-3
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 16, 16, 256), (1, 5, 7, 256), (40, 8, 8, 256)])
+def test_groupnorm_act_conv1x1_matches_torch(dtype, shape):
+    """Decoder tail fused: GN(32) -> GELU -> Conv1x1 256 -> 3 + bias (xyz_head.py:349-366)."""
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    x = (torch.randn(*shape, generator=g) * 2 + 0.5).to(dtype)
+    gam, bet = torch.rand(256, generator=g) + 0.5, torch.randn(256, generator=g) * 0.1
+    w, b = torch.randn(3, 256, generator=g) * 0.05, torch.randn(3, generator=g) * 0.1
+    y = F.gelu(F.group_norm(x.float().permute(0, 3, 1, 2), 32, gam, bet, 1e-5))
+    ref = F.conv2d(y, w.view(3, 256, 1, 1), b).permute(0, 2, 3, 1)
+    got = ops.groupnorm_act_conv1x1(x.cuda(), gam.cuda(), bet.cuda(), w.cuda(), b.cuda(), 32, 1e-5, "gelu")
+    assert got.shape == ref.shape and got.dtype == dtype
+    assert rel(got, ref) < (5e-6 if dtype == torch.float32 else 6e-3)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_stem_s2d_pack_and_conv_equal_the_direct_stem(dtype):
+    """The 7x7/2 stem as a 4x4/1 convolution over the packed space-to-depth operand: the packing is exact (bit-exact vs torch's
+    pixel_unshuffle + pad), the convolution equals the direct one up to summation order."""
+    from givepose_b200 import ops
+    from givepose_b200.posenet import ResNet34Backbone, _stem, _stem_s2d
+    g = torch.Generator().manual_seed(11)
+    img = torch.randn(3, 3, 64, 48, generator=g)
+    packed = ops.stem_s2d_pack(img.cuda(), dtype)
+    ref = F.pad(F.pixel_unshuffle(img, 2), (2, 1, 2, 1, 0, 4)).permute(0, 2, 3, 1).to(dtype)
+    assert packed.shape == (3, 35, 27, 16) and torch.equal(packed.cpu(), ref)
+    torch.manual_seed(0)
+    bb = ResNet34Backbone().cuda().eval()
+    old_tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False   # the fp32 parity mode of PoseNet runs with TF32 off
+    try:
+        with torch.no_grad():
+            bb.trunk.bn1.running_mean.normal_(std=0.1)
+            bb.trunk.bn1.running_var.uniform_(0.5, 1.5)
+            a = _stem_s2d(img.cuda(), bb.trunk.conv1, bb.trunk.bn1, dtype)
+            b = _stem(img.cuda().to(dtype).contiguous(memory_format=torch.channels_last), bb.trunk.conv1, bb.trunk.bn1)
+    finally:
+        torch.backends.cudnn.allow_tf32 = old_tf32
+    assert a.shape == b.shape == (3, 64, 16, 12) and rel(a, b) < (2e-6 if dtype == torch.float32 else 2e-2)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_maxpool_and_upsample_match_torch(dtype):
     from givepose_b200 import ops
@@ -112,6 +171,27 @@ def test_dcnv3_module_fused_equals_unfused(OP):
         unfused = m(x.clone().requires_grad_(True))
     assert fused.shape == (8, 16, 16, 256) and rel(fused, unfused.detach()) < 2e-5
     unfused.square().mean().backward()   # the training path is differentiable end to end
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 5e-2)])
+def test_first_encoder_layer_composed_equals_op_sequence(dtype, tol):
+    """DCNv3_C with 3 input channels (network/dcnv3.py:32-38): input_proj o conv and dw_conv o conv composed, the
+    256-channel conv output never written -- equals conv -> DCNv3 evaluated op by op (fp32, unfused torch glue)."""
+    from givepose_b200.posenet import DCNv3_C, _conv1x1_rows
+    torch.manual_seed(1)
+    m = DCNv3_C(3, 256, kernel_size=3, stride=2).cuda()
+    with torch.no_grad():
+        m.conv.bias.normal_(std=0.2)
+        m.dcnv3.dw_conv[0].bias.normal_(std=0.1)
+        for lin in (m.dcnv3.offset, m.dcnv3.mask):
+            lin.weight.normal_(std=0.08)
+            lin.bias.normal_(std=0.3)
+    x = torch.rand(8, 32, 32, 3, device="cuda") - 0.5
+    with torch.enable_grad():   # op-by-op reference path: differentiable torch glue around DCNv3Function, fp32
+        ref = m.dcnv3(_conv1x1_rows(x, m.conv)).detach()
+    with torch.no_grad():
+        got = m.forward_nhwc(x.to(dtype))   # parameters stay fp32 masters; 16-bit runs use cached weight copies
+    assert got.shape == (8, 16, 16, 256) and rel(got, ref) < tol
 
 
 @pytest.mark.parametrize("mode", ["reference", "o1"])
