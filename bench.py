@@ -231,20 +231,22 @@ def run_posenet(args, rank, world, dev, dist):
     if args.train_rois > 0:
         # BASELINE configs[4]: data-parallel training step, `train_rois` RoIs per GPU (reference batch_size 48, config.py:42),
         # bf16 autocast over fp32 master weights, ONE NCCL all-reduce of the flat fp32 gradient bucket per step
-        from givepose_b200.train import GradBucket, make_targets, train_step
+        from givepose_b200.loss import PoseLoss, make_loss_inputs
+        from givepose_b200.train import GradBucket, train_step
         _, net = build_posenet("bf16", dev)
         tb = args.train_rois
         tdata = {k: v.to(dev) for k, v in posenet_inputs(tb, seed=100 + rank).items()}
-        tgt = make_targets(tb, dev, seed=rank)
+        tgt = {k: v.to(dev) for k, v in make_loss_inputs(tb, seed=rank).items()}
+        crit = PoseLoss().to(dev)
         opt = torch.optim.SGD(net.parameters(), lr=1e-5, momentum=0.9)
         bucket = GradBucket(net.parameters())
         for _ in range(2):
-            train_step(net, tdata, tgt, opt, bucket, dev)
+            train_step(net, tdata, tgt, opt, bucket, dev, criterion=crit)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(args.posenet_steps):
-            loss = train_step(net, tdata, tgt, opt, bucket, dev)
+            loss = train_step(net, tdata, tgt, opt, bucket, dev, criterion=crit)
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1) / args.posenet_steps], device=dev, dtype=torch.float64)
@@ -253,7 +255,7 @@ def run_posenet(args, rank, world, dev, dist):
         out["train_step"] = {"value": round(tb * world / (t.item() * 1e-3), 1), "unit": "RoIs/s", "rois_per_gpu": tb, "scaling": "weak",
                              "ms_per_step": round(t.item(), 3), "dtype": "bf16 autocast, fp32 master weights + grads",
                              "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum)/world, one flat bucket" if world > 1 else "none (1 rank)",
-                             "loss": "surrogate L1 / smooth-L1 (reference PoseLoss is out of scope this round)", "last_loss": round(float(loss), 5)}
+                             "loss": "givepose_b200.loss.PoseLoss (reference losses/pose_loss.py terms, batched on device, 1/3 symmetric RoIs)", "last_loss": round(float(loss), 5)}
         del net, opt, bucket
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

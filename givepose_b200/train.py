@@ -36,7 +36,9 @@ def shard_batch(data: Dict[str, torch.Tensor], rank: int, world: int) -> Dict[st
 
 
 class GradBucket:
-    """One flat fp32 buffer for all trainable parameters' gradients -> a single all-reduce per step."""
+    """One flat fp32 buffer that IS the gradient storage of every trainable parameter (``p.grad`` are views into it, autograd
+    accumulates in place) -> zeroing is one memset, the all-reduce one collective, and nothing is copied in or out.
+    Parameters that never receive a gradient (``DCNv3_C.bn``) simply keep zeros."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter]):
         self.params = [p for p in params if p.requires_grad]
@@ -48,27 +50,36 @@ class GradBucket:
         for p in self.params:
             self.views.append(self.flat[o:o + p.numel()].view_as(p))
             o += p.numel()
+        self.attach()
+
+    def attach(self) -> None:
+        """(Re)install the views as ``p.grad`` -- needed after anything that replaced them (``zero_grad(set_to_none=True)``)."""
+        for p, v in zip(self.params, self.views):
+            if p.dtype == torch.float32 and p.grad is not v:
+                p.grad = v
+
+    def zero_(self) -> None:
+        self.attach()
+        self.flat.zero_()
 
     def nbytes(self) -> int:
         return self.numel * 4
 
     @torch.no_grad()
     def allreduce_(self, group=None) -> None:
-        """grads -> flat buffer (zeros where ``grad is None``) -> all_reduce(sum) / world -> back into ``p.grad``."""
+        """all_reduce(sum) / world of the flat buffer; gradients that autograd placed elsewhere (non-fp32 parameters, a
+        replaced ``p.grad``) are folded in first."""
         world = dist.get_world_size(group) if dist.is_initialized() else 1
         for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                v.zero_()
-            else:
+            if p.grad is not None and p.grad is not v:
                 v.copy_(p.grad)
+                p.grad = v if p.dtype == torch.float32 else p.grad
         if world > 1:
             dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group)
             self.flat.div_(world)
-        for p, v in zip(self.params, self.views):
-            if p.grad is None:
-                p.grad = v.clone()
-            else:
-                p.grad.copy_(v)
+            for p, v in zip(self.params, self.views):
+                if p.grad is not None and p.grad is not v:
+                    p.grad.copy_(v)
 
 
 def surrogate_loss(out: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> torch.Tensor:
@@ -86,15 +97,18 @@ def make_targets(B: int, device, seed: int = 0) -> Dict[str, torch.Tensor]:
                                          "nocs_coor": r(B, 3, 64, 64) * 0.3, "ivfc_coor": r(B, 3, 64, 64) * 0.3}.items()}
 
 
-def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: float = 5.0, group=None) -> float:
+def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: float = 5.0, group=None, criterion=None) -> float:
     """One data-parallel step on this rank's shard: forward (autograd path: torch CUDA ops around ``DCNv3Function``) ->
-    loss -> backward (DCNv3 backward kernel) -> gradient all-reduce -> clip (``engine/train.py:126``) -> step."""
+    loss -> backward (DCNv3 backward kernel) -> gradient all-reduce -> clip (``engine/train.py:126``) -> step.
+
+    ``criterion``: a ``givepose_b200.loss.PoseLoss`` -- then ``target`` is the ground-truth dict of the reference's data
+    loader and the loss is the sum of its terms as in ``engine/train.py:120-122``; ``None`` keeps the simple surrogate."""
     net.train()
-    optimizer.zero_grad(set_to_none=True)
+    bucket.zero_()   # p.grad are views of the flat buffer: one memset instead of optimizer.zero_grad()
     data = dict(data)
     data.setdefault("roi_mask_deform", data["roi_mask"])
     out = net(data, device, do_loss=True)
-    loss = surrogate_loss(out, target)
+    loss = surrogate_loss(out, target) if criterion is None else sum(criterion(out, target).values())
     loss.backward()
     bucket.allreduce_(group)
     torch.nn.utils.clip_grad_norm_(bucket.params, clip)

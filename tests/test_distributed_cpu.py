@@ -59,7 +59,13 @@ def _worker(rank, world, port, out):
         ref_net.load_state_dict(net.state_dict())
         ref_net(x).square().sum().backward()
         ref = torch.cat([p.grad.flatten() for p in ref_net.parameters()] + [torch.zeros(6)]) / world
-        out[rank] = (torch.allclose(flat, ref, atol=1e-6), bucket.nbytes())
+        ok = torch.allclose(flat, ref, atol=1e-6) and all(p.grad.data_ptr() == v.data_ptr() for p, v in zip(bucket.params, bucket.views))
+        # second step: p.grad are views of the flat buffer, zeroing is one memset and autograd accumulates in place
+        bucket.zero_()
+        net(x[lo:hi]).square().sum().backward()
+        bucket.allreduce_()
+        ok = ok and torch.allclose(bucket.flat, ref, atol=1e-6)
+        out[rank] = (ok, bucket.nbytes())
     finally:
         dist.destroy_process_group()
 
