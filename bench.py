@@ -89,14 +89,17 @@ class ClockSampler:
         time.sleep(0.15)
         self.proc.terminate()
         self.t.join(timeout=2)
-        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        num = lambda v: v.replace(".", "", 1).isdigit()
+        good = [r for r in self.rows if len(r) >= 8 and num(r[1]) and num(r[2])]
+        sm, mx = [float(r[1]) for r in good], [float(r[2]) for r in good]
+        pw = [float(r[3]) if num(r[3]) else 0.0 for r in good]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 8 for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
-        # the busiest samples are the ones taken under load
-        sm_load = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        reasons = sorted({n for r in good for n, v in zip(names, r[4:8]) if v.lower().startswith("active")})
+        # samples taken under load = those drawing at least half of the highest power seen in the window
+        load = [c for c, p in zip(sm, pw) if p >= 0.5 * max(pw)] if pw and max(pw) > 0 else sm
+        return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm), "samples_under_load": len(load),
+                "power_w_max": round(max(pw), 1) if pw else None}
 
 
 def cpu_port_step(inp, off, m, gout):
@@ -423,8 +426,13 @@ def main():
     posenet = None
     if not args.no_posenet:
         launches_before = int(lib.gp_launch_count())
+        psampler = ClockSampler(local_rank)
+        if rank == 0:
+            psampler.start()
         posenet = run_posenet(args, rank, world, dev, dist)
         posenet["gpu_launches_total"] = int(lib.gp_launch_count()) - launches_before
+        if rank == 0:
+            posenet["clocks"] = psampler.stop()   # GEMM-heavy section: sw_power_cap is expected here and is kept
 
     if rank != 0:
         if world > 1:

@@ -99,7 +99,8 @@ static bool plan_tiled(KParams &p, int dtype, int *L_out, int *vec_out, bool bac
 }
 
 static size_t tile_smem(const KParams &p, bool softmax) {
-    return (size_t)p.tile_h * p.tile_w * p.gs * (p.P * 24 + 4 + (softmax ? 8 : 0));
+    (void)softmax;   // the fused softmax lives in the builder thread's registers
+    return (size_t)p.tile_h * p.tile_w * p.gs * (p.P * 24 + 4);
 }
 static unsigned tile_grid(const KParams &p) { return (unsigned)((long long)p.N * p.tiles_y * p.tiles_x * p.gchunks); }
 

@@ -5,7 +5,35 @@ using namespace gp;
 
 static bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// slab decomposition shared by the channel-last elementwise kernels: grid (slabs, N), >= 32 pixels per CTA
+static dim3 slab_grid(int N, int npix, int ctas_per_sm, int *ppc) {
+    int slabs = (int)((148ll * ctas_per_sm + N - 1) / N);
+    if (slabs > (npix + 31) / 32) slabs = (npix + 31) / 32;
+    if (slabs < 1) slabs = 1;
+    *ppc = (npix + slabs - 1) / slabs;
+    return dim3((npix + *ppc - 1) / *ppc, N);
+}
+
+// statistics passes shared by the two GroupNorm entry points: partials -> (mean, rstd) in stats[0 .. N*G*2)
+template <typename T>
+static void gn_statistics(const void *x, float *stats, int N, int HW, int C, int G, float eps, cudaStream_t st) {
+    int ppc = 0;
+    const dim3 sgrid = slab_grid(N, HW, 8, &ppc);
+    float *partial = stats + (size_t)N * G * 2;
+    gn_stats_kernel<T><<<sgrid, 256, 256 * 2 * sizeof(float), st>>>((const T *)x, partial, HW, C, G, ppc);
+    gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(partial, stats, N * G, G, (int)sgrid.x, 1.f / ((float)HW * (C / G)), eps);
+    count_launch(2);
+}
+
 extern "C" {
+
+size_t gp_groupnorm_workspace_floats(int N, int H, int W, int G) {
+    if (N <= 0 || H <= 0 || W <= 0 || G <= 0) return 0;
+    int ppc = 0;
+    const dim3 sgrid = slab_grid(N, H * W, 8, &ppc);
+    return (size_t)N * G * 2 * (1 + sgrid.x);   // (mean, rstd) per (n, g) followed by the slab partials
+}
+
 
 int gp_dwconv3x3_ln_gelu(const void *x, const float *w_t, const float *bias, const float *ln_w, const float *ln_b, void *out,
                          int N, int H, int W, int C, long long rows, float eps, int dtype, void *stream) {
@@ -79,30 +107,20 @@ int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *
     return (int)cudaGetLastError();
 }
 
-// slab decomposition shared by the channel-last elementwise kernels: grid (slabs, N), >= 32 pixels per CTA
-static dim3 slab_grid(int N, int npix, int ctas_per_sm, int *ppc) {
-    int slabs = (int)((148ll * ctas_per_sm + N - 1) / N);
-    if (slabs > (npix + 31) / 32) slabs = (npix + 31) / 32;
-    if (slabs < 1) slabs = 1;
-    *ppc = (npix + slabs - 1) / slabs;
-    return dim3((npix + *ppc - 1) / *ppc, N);
-}
-
-int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, const float *beta, int N, int H, int W, int C,
-                     int G, float eps, int act, int dtype, void *stream) {
+int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N, int H,
+                     int W, int C, int G, float eps, int act, int dtype, void *stream) {
     if (!x || !y || !stats || !gamma || !beta) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || C % G || (C / G) % 4 || C / 4 > 256) return GP_ERR_SHAPE;
     if (act < 0 || act > 2) return GP_ERR_UNSUPPORTED;
     if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
+    if (stats_floats < gp_groupnorm_workspace_floats(N, H, W, G)) return GP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t ce = cudaMemsetAsync(stats, 0, (size_t)N * G * 2 * sizeof(float), st);
-    if (ce != cudaSuccess) return (int)ce;
     const int HW = H * W;
-    int ppc = 0, appc = 0;
-    const dim3 sgrid = slab_grid(N, HW, 8, &ppc), agrid = slab_grid(N, HW, 16, &appc);
+    int appc = 0;
+    const dim3 agrid = slab_grid(N, HW, 16, &appc);
 #define GP_GN_APPLY(TT, AA) gn_apply_kernel<TT, AA><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, (TT *)y, HW, C, G, eps, appc)
-#define GP_GN(TT) do { gn_stats_kernel<TT><<<sgrid, 256, 2 * G * sizeof(float), st>>>((const TT *)x, stats, HW, C, G, ppc); \
+#define GP_GN(TT) do { gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
                        if (act == ACT_RELU) GP_GN_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GN_APPLY(TT, ACT_GELU); \
                        else GP_GN_APPLY(TT, ACT_NONE); } while (0)
     switch (dtype) {
@@ -113,25 +131,24 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, c
     }
 #undef GP_GN
 #undef GP_GN_APPLY
-    count_launch(2);
+    count_launch();
     return (int)cudaGetLastError();
 }
 
-int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, const float *gamma, const float *beta, const float *w,
-                             const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC, int dtype,
-                             void *stream) {
+int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                             const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                             int dtype, void *stream) {
     if (!x || !y || !stats || !gamma || !beta || !w || !bias) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || G <= 0 || C % G || (C / G) % 4) return GP_ERR_SHAPE;
     if (C != 256 || OC != 3 || act < 0 || act > 2) return GP_ERR_UNSUPPORTED;   // the decoder's out_layer
     if (!al16(x) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
+    if (stats_floats < gp_groupnorm_workspace_floats(N, H, W, G)) return GP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
-    cudaError_t ce = cudaMemsetAsync(stats, 0, (size_t)N * G * 2 * sizeof(float), st);
-    if (ce != cudaSuccess) return (int)ce;
     const int HW = H * W;
-    int ppc = 0, appc = 0;
-    const dim3 sgrid = slab_grid(N, HW, 8, &ppc), agrid = slab_grid(N, HW, 8, &appc);
+    int appc = 0;
+    const dim3 agrid = slab_grid(N, HW, 8, &appc);
 #define GP_GNC_APPLY(TT, AA) gn_act_conv1x1_kernel<TT, AA, 8, 3><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, w, bias, (TT *)y, HW, G, eps, appc)
-#define GP_GNC(TT) do { gn_stats_kernel<TT><<<sgrid, 256, 2 * G * sizeof(float), st>>>((const TT *)x, stats, HW, C, G, ppc); \
+#define GP_GNC(TT) do { gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
                         if (act == ACT_RELU) GP_GNC_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GNC_APPLY(TT, ACT_GELU); \
                         else GP_GNC_APPLY(TT, ACT_NONE); } while (0)
     switch (dtype) {
@@ -142,7 +159,7 @@ int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, const float *
     }
 #undef GP_GNC
 #undef GP_GNC_APPLY
-    count_launch(2);
+    count_launch();
     return (int)cudaGetLastError();
 }
 
@@ -195,6 +212,23 @@ int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu
         case GP_F32: maxpool3x3s2_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
         case GP_BF16: maxpool3x3s2_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
         case GP_F16: maxpool3x3s2_kernel<__half><<<grid, 256, 0, st>>>((const __half *)x, (__half *)y, H, W, C, ppc, relu ? 0.f : -INFINITY); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_mhsa_tokens(const void *qkv, void *out, int B, int NT, int NH, int HD, float scale, int dtype, void *stream) {
+    if (!qkv || !out) return GP_ERR_NULL;
+    if (B < 0 || B > 65535 || NH <= 0 || NH > 65535) return GP_ERR_SHAPE;
+    if (NT != 64 || HD != 32) return GP_ERR_UNSUPPORTED;   // MAPTransformerEncoer: 8x8 patches, 256 / 8 heads
+    if (B == 0) return GP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const dim3 grid(NH, B);
+    switch (dtype) {
+        case GP_F32: mhsa_tokens_kernel<float, 64, 32><<<grid, 64, 0, st>>>((const float *)qkv, (float *)out, NH, scale); break;
+        case GP_BF16: mhsa_tokens_kernel<__nv_bfloat16, 64, 32><<<grid, 64, 0, st>>>((const __nv_bfloat16 *)qkv, (__nv_bfloat16 *)out, NH, scale); break;
+        case GP_F16: mhsa_tokens_kernel<__half, 64, 32><<<grid, 64, 0, st>>>((const __half *)qkv, (__half *)out, NH, scale); break;
         default: return GP_ERR_DTYPE;
     }
     count_launch();

@@ -72,87 +72,121 @@ __device__ __forceinline__ TileCtx decode_tile(const KParams &p) {
     return t;
 }
 
-constexpr unsigned F_ALL = 32u;   // all four corners inside the image (fast path: four unpredicated loads)
+constexpr unsigned F_ALL = 32u;   // backward records: all four corners inside the image (four unpredicated loads / reductions)
+constexpr unsigned FW_SX = 1u;    // forward records: both columns of the 2x2 footprint are inside the image
+constexpr unsigned FW_SY = 2u;    //                  both rows are
+constexpr unsigned FW_OUT = 4u;   // build-time marker of an out-of-range sample (never seen by the sampling loop)
 
-// One record per (unit, point), built ONCE per CTA by one thread and then read (LDS broadcast) by the L lanes
-// that own the unit's channels, so the coordinate arithmetic (locate(), the same device function the index
-// hook runs) is not repeated per channel as in the reference kernel (cuh:249-269 run by every thread).
-//   s_bf[r] = { BYTE offset of corner 1 relative to (image, group), flags }      flags == 0: out of range
-//   s_w [r] = forward : { w1, w2, w3, w4 } * mask, 0 for corners outside the image
-//             backward: { lh, lw, mask, - }; after the unit is processed { grad_off_w, grad_off_h, grad_mask, - }
-// r = ul*P + pt with ul = g_local*TP + pix (group-major: consecutive passes work on one group's window).
-// smem: n_rec * 24 bytes (+ 8 bytes per unit for the fused softmax).
+// Sampling records, built ONCE per CTA by ONE thread per unit (its P points in a row, so everything that only depends
+// on the unit -- pixel decode, row pointers, p0, the softmax of the fused variant -- is computed once, and for P == 9 the
+// kernel indices are compile-time constants) and then read (LDS broadcast) by the L lanes that own the unit's channels.
+// The reference redoes this arithmetic in every channel thread (cuh:249-269 run by every thread).  locate() is the same
+// device function the index hook runs.  r = ul*P + pt with ul = g_local*TP + pix.
+//
+//   forward   s_bf[r] = { byte offset of the footprint's first VALID pixel relative to (image, group), FW_SX | FW_SY }
+//             s_w [r] = { w1, w2, w3, w4 } * mask, 0 for corners outside the image (cuh:55-76)
+//             The four loads of a point go to base, base + sx, base + sy, base + sx + sy with sx / sy = 0 when that side of
+//             the footprint is outside the image: every address is a pixel the reference reads for this very sample, the
+//             weight of a corner it does not read is 0, so the loop is branch-free for border and interior units alike.
+//             A sample that is out of range altogether (cuh:268-269) gets zero weights and borrows the address of another
+//             sample of its unit; a unit without any in-range sample is marked dead (s_unit[ul] == 0) and writes zeros.
+//   backward  s_bf[r] = { byte offset of corner 1 (may lie outside), F_IN | F_C1..4 | F_ALL },  s_w[r] = { lh, lw, mask, - };
+//             after the unit is processed s_w[r] = { grad_off_w, grad_off_h, grad_mask, - }.  s_unit[ul] != 0 <=> all P points
+//             have all four corners inside.
+// smem: n_rec * 24 bytes + 4 bytes per unit.
 template <typename T, bool SOFTMAX, bool BWD, bool P9>
 __device__ __forceinline__ void build_records(const T *__restrict__ off, const T *__restrict__ msk, float4 *s_w,
-                                              int2 *s_bf, unsigned *s_unit, float *s_red, const KParams &p,
-                                              const TileCtx &t) {
+                                              int2 *s_bf, unsigned *s_unit, const KParams &p, const TileCtx &t) {
     const int P = P9 ? 9 : p.P;
-    // s_unit[ul] != 0  <=>  every sampling point of the unit has all four corners inside the image
-    for (int ul = threadIdx.x; ul < t.n_ul; ul += blockDim.x) {
-        s_unit[ul] = 1u;
-        if (SOFTMAX) {   // softmax over the P logits of each (pixel, group) row: modules/dcnv3.py:332-333
-            const UnitPos u = unit_pos(ul, p, t);
-            float mx = 0.f, inv = 0.f;
-            if (u.oh < p.Ho && u.ow < p.Wo) {
-                const long long q = ((long long)t.b * p.Ho + u.oh) * p.Wo + u.ow;
-                const T *row = msk + (q * p.G + t.g0 + u.gl) * (long long)P;
-                mx = to_acc<T>(row[0]);
-                for (int i = 1; i < P; ++i) mx = fmaxf(mx, to_acc<T>(row[i]));
-                float sum = 0.f;
-                for (int i = 0; i < P; ++i) sum += expf(to_acc<T>(row[i]) - mx);
-                inv = 1.f / sum;
-            }
-            s_red[2 * ul] = mx;
-            s_red[2 * ul + 1] = inv;
-        }
-    }
-    __syncthreads();
     const int cidx = (p.kw / 2) * p.kh + p.kh / 2;   // the centre point in the full kw*kh enumeration
     const int C = p.C, WC = p.W * C;
-    const int n_rec = t.n_ul * P;
-    for (int e = threadIdx.x; e < n_rec; e += blockDim.x) {
-        // e enumerates (pix, g_local, pt) with pt fastest: global-memory order within a pixel row
-        const int pg = e / P, pt = e - pg * P;
-        const int pix = pg >> p.lg_gs, gl = pg & (p.gs - 1);
+    // e enumerates (pix, g_local) with g_local fastest: global-memory order of the offset / mask rows
+    for (int e = threadIdx.x; e < t.n_ul; e += blockDim.x) {
+        const int pix = e >> p.lg_gs, gl = e & (p.gs - 1);
         const int oh = t.oh0 + (pix >> p.lg_tw), ow = t.ow0 + (pix & (p.tile_w - 1));
         const int ul = gl * t.TP + pix;
-        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-        int2 bf = make_int2(0, 0);
-        if (oh < p.Ho && ow < p.Wo) {
-            const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-            const long long k = ((q * p.G + t.g0 + gl) * (long long)P) + pt;   // (q*G+g)*P + pt, cuh:243-244
+        if (oh >= p.Ho || ow >= p.Wo) {   // tile overhang: the sampling loop never visits this unit
+            s_unit[ul] = 0u;
+            continue;
+        }
+        const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
+        const long long row = (q * p.G + t.g0 + gl) * (long long)P;   // (q*G+g)*P, cuh:243-244
+        const T *orow = off + 2 * row, *mrow = msk + row;
+        const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
+        const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
+        float mx = 0.f, inv = 1.f;
+        if (SOFTMAX) {   // softmax over the P logits of the (pixel, group) row: modules/dcnv3.py:332-333
+            mx = to_acc<T>(__ldg(mrow));
+            for (int i = 1; i < P; ++i) mx = fmaxf(mx, to_acc<T>(__ldg(mrow + i)));
+            float sum = 0.f;
+            for (int i = 0; i < P; ++i) sum += expf(to_acc<T>(__ldg(mrow + i)) - mx);
+            inv = 1.f / sum;
+        }
+        float4 *rw = s_w + ul * P;
+        int2 *rb = s_bf + ul * P;
+        unsigned interior = 1u, out_mask = 0u;
+        int ubase = -1;
+        auto one_point = [&](int pt, int i, int j) {   // p = i*kh + j, kernel WIDTH index i is the slow one (cuh:257-258)
             float ox, oy;
-            load_pair<T>(off + 2 * k, ox, oy);   // (w, h) pair, cuh:261-262
-            float m = to_acc<T>(__ldg(msk + k));
-            if (SOFTMAX) m = expf(m - s_red[2 * ul]) * s_red[2 * ul + 1];
-            int i, j;   // p = i*kh + j, kernel WIDTH index i is the slow one (cuh:257-258)
-            if (P9) {
-                i = pt / 3; j = pt - i * 3;
+            load_pair<T>(orow + 2 * pt, ox, oy);   // (w, h) pair, cuh:261-262
+            float m = to_acc<T>(__ldg(mrow + pt));
+            if (SOFTMAX) m = expf(m - mx) * inv;
+            Point<float> sp;
+            locate<float>(sp, p0_h_, p0_w_, j * p.dh, i * p.dw, ox, oy, p.scale, p.H, p.W);
+            float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+            int2 bf = make_int2(0, 0);
+            if (BWD) {
+                if (sp.flags & F_IN) {
+                    bf.x = (sp.h_low * WC + sp.w_low * C) * (int)sizeof(T);
+                    bf.y = (int)(sp.flags | ((sp.flags & 30u) == 30u ? F_ALL : 0u));
+                    w = make_float4(sp.lh, sp.lw, m, 0.f);
+                }
+                if (!(bf.y & (int)F_ALL)) interior = 0u;
+            } else if (sp.flags & F_IN) {
+                // cuh:76 weights, mask folded in; corners outside the image contribute 0 (cuh:55-75)
+                w.x = (sp.flags & F_C1) ? sp.hh * sp.hw * m : 0.f;
+                w.y = (sp.flags & F_C2) ? sp.hh * sp.lw * m : 0.f;
+                w.z = (sp.flags & F_C3) ? sp.lh * sp.hw * m : 0.f;
+                w.w = (sp.flags & F_C4) ? sp.lh * sp.lw * m : 0.f;
+                const bool hl = sp.h_low >= 0, wl = sp.w_low >= 0;
+                const bool hh = sp.h_low + 1 <= p.H - 1, wh = sp.w_low + 1 <= p.W - 1;
+                const int r0 = hl ? sp.h_low : sp.h_low + 1, c0 = wl ? sp.w_low : sp.w_low + 1;
+                bf.x = (r0 * WC + c0 * C) * (int)sizeof(T);
+                bf.y = (int)((wl && wh ? FW_SX : 0u) | (hl && hh ? FW_SY : 0u));
+                if (ubase < 0) ubase = bf.x;
             } else {
+                out_mask |= 1u << (pt & 31);
+                bf.y = (int)FW_OUT;   // marker for the borrow pass below (cleared there)
+            }
+            rw[pt] = w;
+            rb[pt] = bf;
+        };
+        if (P9) {
+#pragma unroll
+            for (int pt = 0; pt < 9; ++pt) one_point(pt, pt / 3, pt % 3);
+        } else {
+            for (int pt = 0; pt < P; ++pt) {
                 int kk = pt;
                 if (p.remove_center && kk >= cidx) ++kk;
-                i = kk / p.kh; j = kk - i * p.kh;
+                const int i = kk / p.kh;
+                one_point(pt, i, kk - i * p.kh);
             }
-            const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
-            const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
-            Point<float> s;
-            locate<float>(s, p0_h_, p0_w_, j * p.dh, i * p.dw, ox, oy, p.scale, p.H, p.W);
-            if (s.flags & F_IN) {
-                bf.x = (s.h_low * WC + s.w_low * C) * (int)sizeof(T);
-                bf.y = (int)(s.flags | ((s.flags & 30u) == 30u ? F_ALL : 0u));
-                if (BWD) {
-                    w = make_float4(s.lh, s.lw, m, 0.f);
-                } else {   // cuh:76 weights, mask folded in; corners outside the image contribute 0 (cuh:55-75)
-                    w.x = (s.flags & F_C1) ? s.hh * s.hw * m : 0.f;
-                    w.y = (s.flags & F_C2) ? s.hh * s.lw * m : 0.f;
-                    w.z = (s.flags & F_C3) ? s.lh * s.hw * m : 0.f;
-                    w.w = (s.flags & F_C4) ? s.lh * s.lw * m : 0.f;
+        }
+        if (BWD) {
+            s_unit[ul] = interior;
+        } else {
+            s_unit[ul] = ubase >= 0 ? 1u : 0u;
+            if (ubase >= 0 && out_mask) {   // out-of-range samples borrow an address this unit reads anyway (their weights are 0)
+                if (P9) {
+#pragma unroll
+                    for (int pt = 0; pt < 9; ++pt)
+                        if (out_mask & (1u << pt)) rb[pt] = make_int2(ubase, 0);
+                } else {
+                    for (int pt = 0; pt < P; ++pt)
+                        if (rb[pt].y == (int)FW_OUT) rb[pt] = make_int2(ubase, 0);
                 }
             }
         }
-        if (!(bf.y & (int)F_ALL)) s_unit[ul] = 0u;   // benign race: every writer stores 0
-        s_w[ul * P + pt] = w;
-        s_bf[ul * P + pt] = bf;
     }
     __syncthreads();
 }
@@ -192,12 +226,11 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     float4 *s_w = smem4;
     int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
     unsigned *s_unit = reinterpret_cast<unsigned *>(s_bf + n_rec);
-    float *s_red = reinterpret_cast<float *>(s_unit + t.n_ul);
-    build_records<T, SOFTMAX, false, P9>(off, msk, s_w, s_bf, s_unit, s_red, p, t);
+    build_records<T, SOFTMAX, false, P9>(off, msk, s_w, s_bf, s_unit, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;
-    const int Cb = C * (int)sizeof(T), WCb = WC * (int)sizeof(T);
+    const unsigned Cb = (unsigned)(C * (int)sizeof(T)), WCb = (unsigned)(WC * (int)sizeof(T));
     const T *in_b = in + (long long)t.b * p.H * WC + cl * VEC;
     constexpr int UPB = kTileThreads / L;   // units per pass
 
@@ -205,10 +238,7 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     for (int pass = 0; pass < n_pass; ++pass) {
         const int ul = pass * UPB + threadIdx.x / L;
         const UnitPos u = unit_pos(ul, p, t);
-        const bool valid = ul < t.n_ul && u.oh < p.Ho && u.ow < p.Wo;
-        // one decision per warp: a mixed warp would otherwise run the branch-free and the careful loop back to back
-        const bool fast = P9 && __all_sync(0xffffffffu, valid && s_unit[valid ? ul : 0]);
-        if (!valid) continue;
+        if (!(ul < t.n_ul && u.oh < p.Ho && u.ow < p.Wo)) continue;
         const int g = t.g0 + u.gl;
         const char *in_g = reinterpret_cast<const char *>(in_b + g * p.gc);
         const float4 *rw = s_w + ul * P;
@@ -218,35 +248,31 @@ dcnv3_fwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
 #pragma unroll
         for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
 
-        // (w1 v1 + w2 v2 + w3 v3 + w4 v4) * mask, cuh:78 + :270-273 (mask folded into the record's weights)
-        auto accumulate = [&](const float4 w, const float (&v1)[VEC], const float (&v2)[VEC], const float (&v3)[VEC],
-                              const float (&v4)[VEC]) {
+        // (w1 v1 + w2 v2 + w3 v3 + w4 v4) * mask, cuh:78 + :270-273 (mask folded into the record's weights); four
+        // unconditional gathers per point, no branches -> the scheduler overlaps points freely
+        auto point = [&](int k) {
+            const int2 bf = rb[k];
+            const float4 w = rw[k];
+            const unsigned fx = (unsigned)bf.y & FW_SX, fy = (unsigned)bf.y >> 1;
+            const char *p1 = in_g + (unsigned)bf.x;
+            const char *p2 = p1 + (size_t)fx * Cb;
+            const char *p3 = p1 + (size_t)fy * WCb;
+            const char *p4 = p3 + (size_t)fx * Cb;
+            float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
+            Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
+            Vec<T, VEC>::load(reinterpret_cast<const T *>(p2), v2);
+            Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
+            Vec<T, VEC>::load(reinterpret_cast<const T *>(p4), v4);
 #pragma unroll
             for (int c = 0; c < VEC; ++c)
                 acc[c] = fmaf(w.x, v1[c], fmaf(w.y, v2[c], fmaf(w.z, v3[c], fmaf(w.w, v4[c], acc[c]))));
         };
-
-        if (fast) {
-            // interior unit: 36 unconditional gathers, no branches -> the scheduler overlaps points freely
+        if (s_unit[ul]) {   // a unit whose samples are all out of range reads nothing and writes zeros (cuh:268-269)
+            if (P9) {
 #pragma unroll
-            for (int k = 0; k < 9; ++k) {
-                const char *p1 = in_g + rb[k].x, *p3 = p1 + WCb;
-                const float4 w = rw[k];
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1), v1);
-                Vec<T, VEC>::load(reinterpret_cast<const T *>(p1 + Cb), v2);
-                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3), v3);
-                Vec<T, VEC>::load(reinterpret_cast<const T *>(p3 + Cb), v4);
-                accumulate(w, v1, v2, v3, v4);
-            }
-        } else {
-            for (int k = 0; k < P; ++k) {
-                const int2 bf = rb[k];
-                if (bf.y == 0) continue;   // sample out of range: contributes nothing (cuh:268-269)
-                const float4 w = rw[k];
-                float v1[VEC], v2[VEC], v3[VEC], v4[VEC];
-                gather4<T, VEC>(in_g + bf.x, Cb, WCb, (unsigned)bf.y, v1, v2, v3, v4);
-                accumulate(w, v1, v2, v3, v4);
+                for (int k = 0; k < 9; ++k) point(k);
+            } else {
+                for (int k = 0; k < P; ++k) point(k);
             }
         }
         const long long q = ((long long)t.b * p.Ho + u.oh) * p.Wo + u.ow;
@@ -356,7 +382,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
     float4 *s_w = smem4;
     int2 *s_bf = reinterpret_cast<int2 *>(s_w + n_rec);
     unsigned *s_unit = reinterpret_cast<unsigned *>(s_bf + n_rec);
-    build_records<T, false, true, P9>(off, msk, s_w, s_bf, s_unit, nullptr, p, t);
+    build_records<T, false, true, P9>(off, msk, s_w, s_bf, s_unit, p, t);
 
     const int cl = threadIdx.x % L;
     const int C = p.C, WC = p.W * C;

@@ -259,8 +259,9 @@ smallk_dwconv_ln_gelu_kernel(const T *__restrict__ x /*(N,H,W,K)*/, const float 
 
 // ---------------------------------------------------------------------------------------------------
 // GroupNorm on channel-last activations (N, HW, C), G groups of cg = C/G channels.
-//   pass 1 (gn_stats): one CTA per (n, slab of pixels): per-group partial sum / sum of squares accumulated in fp32 into
-//           stats[n][g][2] with one atomicAdd pair per (CTA, group)  (stats must be zero on entry)
+//   pass 1 (gn_stats): one CTA per (n, slab of pixels): per-group partial sum / sum of squares in fp32, written to
+//           partial[n][slab][g][2]; gn_finalize turns them into (mean, rstd) per (n, g).  No atomics anywhere: sums are taken
+//           in a fixed order, so the result is bit-reproducible.
 //   pass 2 (gn_apply): y = act((x - mean) * rstd * gamma + beta)
 // The bilinear x2 upsampling that follows GN+GELU in the decoder is its own pass (upsample2x_kernel): fusing it into
 // gn_apply evaluates GELU four times per output element and was measured 5x slower (compute-bound on erf).
@@ -269,14 +270,13 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-gn_stats_kernel(const T *__restrict__ x, float *__restrict__ stats, int HW, int C, int G, int pix_per_cta) {
-    // thread t owns channel quad (t % (C/4)) and strides over the slab's pixels
-    extern __shared__ float s_part[];   // [G][2]
+gn_stats_kernel(const T *__restrict__ x, float *__restrict__ partial /*[N][slabs][G][2]*/, int HW, int C, int G, int pix_per_cta) {
+    // thread t owns channel quad (t % (C/4)) and strides over the slab's pixels; everything is summed in a fixed order
+    // (no atomics): the forward is bit-reproducible run to run
+    extern __shared__ float s_thr[];   // [blockDim][2]
     const int n = blockIdx.y;
     const int q = C / 4, cq = threadIdx.x % q, prow = threadIdx.x / q, pstep = blockDim.x / q;
     const int cg = C / G;
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) s_part[i] = 0.f;
-    __syncthreads();
     const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
     float s = 0.f, ss = 0.f;
     if (prow < pstep)
@@ -289,11 +289,35 @@ gn_stats_kernel(const T *__restrict__ x, float *__restrict__ stats, int HW, int 
                 ss = fmaf(v[k], v[k], ss);
             }
         }
-    const int g = (4 * cq) / cg;   // cg is a multiple of 4 (checked on the host)
-    atomicAdd(&s_part[2 * g], s);
-    atomicAdd(&s_part[2 * g + 1], ss);
+    s_thr[2 * threadIdx.x] = s;
+    s_thr[2 * threadIdx.x + 1] = ss;
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) atomicAdd(&stats[(long long)n * 2 * G + i], s_part[i]);
+    // thread i < 2G: statistic (i & 1) of group (i >> 1) = its cg/4 quads x pstep pixel rows, in index order
+    for (int i = threadIdx.x; i < 2 * G; i += blockDim.x) {
+        const int g = i >> 1, qpg = cg / 4;   // cg is a multiple of 4 (checked on the host)
+        float a = 0.f;
+        for (int r = 0; r < pstep; ++r)
+            for (int j = 0; j < qpg; ++j) a += s_thr[2 * (r * q + g * qpg + j) + (i & 1)];
+        partial[(((long long)n * gridDim.x + blockIdx.x) * G + g) * 2 + (i & 1)] = a;
+    }
+}
+
+// (mean, rstd) per (n, group) from the slab partials, summed in slab order
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats /*[N][G][2]*/, int NG, int G, int slabs, float inv_cnt,
+                   float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NG) return;
+    const int n = i / G, g = i - n * G;
+    float s = 0.f, ss = 0.f;
+    for (int k = 0; k < slabs; ++k) {
+        const float *pp = partial + (((long long)n * slabs + k) * G + g) * 2;
+        s += pp[0];
+        ss += pp[1];
+    }
+    const float mean = s * inv_cnt;
+    stats[2 * i] = mean;
+    stats[2 * i + 1] = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
 }
 
 // GELU for 16-bit storage: 0.5 x (1 + tanh(x (a + b x^2 + c x^4))) with (a, b, c) fitted to the exact erf GELU
@@ -323,13 +347,11 @@ __device__ __forceinline__ void gn_fold(const float *__restrict__ stats, const f
                                         const float *__restrict__ beta, int n, int c0, int C, int G, int HW, float eps,
                                         float (&sc)[V], float (&sh)[V]) {
     const int cg = C / G;
-    const float inv_cnt = 1.f / ((float)HW * cg);
+    (void)HW; (void)eps;   // folded into stats = (mean, rstd) by gn_finalize_kernel
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = c0 + k, g = c / cg;
-        const float s = stats[((long long)n * G + g) * 2], ss = stats[((long long)n * G + g) * 2 + 1];
-        const float mean = s * inv_cnt;
-        const float rstd = rsqrtf(fmaxf(ss * inv_cnt - mean * mean, 0.f) + eps);
+        const float mean = stats[((long long)n * G + g) * 2], rstd = stats[((long long)n * G + g) * 2 + 1];
         sc[k] = rstd * __ldg(gamma + c);
         sh[k] = __ldg(beta + c) - mean * sc[k];
     }
@@ -512,6 +534,56 @@ maxpool3x3s2_kernel(const T *__restrict__ x, T *__restrict__ y, int H, int W, in
         }
         Vec<T, V>::store_stream(out + (long long)p * C, m);
     }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-head self-attention over the NT = 64 patch tokens of MAPTransformerEncoer (attention_pnp_net.py:126-157; timm
+// 0.9.6 `Attention.forward`: softmax(q k^T * hd^-0.5) v per head).  qkv: (B, NT, 3, NH, HD) as produced by the qkv Linear,
+// out: (B, NT, NH*HD).  One CTA per (head, RoI), one thread per query token: K and V of the head sit in shared memory
+// (every thread walks the same row -> broadcast reads), scores / softmax / output row stay in registers, fp32 math.
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int NT, int HD>
+__global__ void __launch_bounds__(NT)
+mhsa_tokens_kernel(const T *__restrict__ qkv, T *__restrict__ out, int NH, float scale) {
+    __shared__ float sK[NT][HD], sV[NT][HD];
+    const int h = blockIdx.x, t = threadIdx.x;
+    const long long b = blockIdx.y;
+    const int row = 3 * NH * HD;
+    const T *base = qkv + b * NT * row + h * HD;
+    float q[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) {
+        q[d] = to_acc<T>(base[(long long)t * row + d]) * scale;
+        sK[t][d] = to_acc<T>(base[(long long)t * row + NH * HD + d]);
+        sV[t][d] = to_acc<T>(base[(long long)t * row + 2 * NH * HD + d]);
+    }
+    __syncthreads();
+    float s[NT], mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        float a = 0.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) a = fmaf(q[d], sK[j][d], a);
+        s[j] = a;
+        mx = fmaxf(mx, a);
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+        s[j] = __expf(s[j] - mx);
+        sum += s[j];
+    }
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+        for (int d = 0; d < HD; ++d) o[d] = fmaf(s[j], sV[j][d], o[d]);
+    const float inv = 1.f / sum;
+    T *dst = out + (b * NT + t) * (long long)(NH * HD) + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; ++d) dst[d] = from_acc<T, float>(o[d] * inv);
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -102,9 +102,9 @@ def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=Fa
     _need_cuda("gn bias", beta, torch.float32)
     N, H, W, C = x.shape
     y = torch.empty_like(x)
-    stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty(lib.gp_groupnorm_workspace_floats(N, H, W, int(groups)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.gp_groupnorm_act(_vp(x), _vp(y), _vp(stats), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
+        check(lib.gp_groupnorm_act(_vp(x), _vp(y), _vp(stats), stats.numel(), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
                                    ACT[act], dt, _stream(x)), "groupnorm_act")
     return upsample_bilinear2x(y) if upsample2x else y
 
@@ -120,11 +120,27 @@ def groupnorm_act_conv1x1(x, gamma, beta, weight, bias, groups=32, eps=1e-5, act
     if weight.shape != (OC, C) or bias.shape != (OC,):
         raise RuntimeError("groupnorm_act_conv1x1: inconsistent weight / bias shapes")
     y = torch.empty((N, H, W, OC), dtype=x.dtype, device=x.device)
-    stats = torch.empty((N, groups, 2), dtype=torch.float32, device=x.device)
+    stats = torch.empty(lib.gp_groupnorm_workspace_floats(N, H, W, int(groups)), dtype=torch.float32, device=x.device)
     with torch.cuda.device(x.device):
-        check(lib.gp_groupnorm_act_conv1x1(_vp(x), _vp(y), _vp(stats), _vp(gamma), _vp(beta), _vp(weight), _vp(bias), N, H, W, C,
+        check(lib.gp_groupnorm_act_conv1x1(_vp(x), _vp(y), _vp(stats), stats.numel(), _vp(gamma), _vp(beta), _vp(weight), _vp(bias), N, H, W, C,
                                            int(groups), float(eps), ACT[act], OC, dt, _stream(x)), "groupnorm_act_conv1x1")
     return y
+
+
+def mhsa_tokens(qkv, num_heads):
+    """Self-attention over the 64 patch tokens of ``MAPTransformerEncoer``: ``qkv`` (B, 64, 3*C) straight from the qkv
+    Linear (timm layout ``(B, N, 3, heads, C/heads)``) -> (B, 64, C)."""
+    _need_cuda("qkv", qkv)
+    dt = _DTYPES.get(qkv.dtype)
+    if dt is None or qkv.dim() != 3 or qkv.shape[2] % (3 * num_heads):
+        raise RuntimeError(f"mhsa_tokens: unsupported input {qkv.dtype} {tuple(qkv.shape)}")
+    B, NT, C3 = qkv.shape
+    C = C3 // 3
+    hd = C // num_heads
+    out = torch.empty((B, NT, C), dtype=qkv.dtype, device=qkv.device)
+    with torch.cuda.device(qkv.device):
+        check(lib.gp_mhsa_tokens(_vp(qkv), _vp(out), B, NT, num_heads, hd, float(hd) ** -0.5, dt, _stream(qkv)), "mhsa_tokens")
+    return out
 
 
 def stem_s2d_pack(img, dtype):

@@ -52,6 +52,7 @@ class PoseNetConfig:
     dataset: str = "Real"         # 'wild6d' rescales z by fx/590 (pose_from_pred_centroid_z.py:110-111)
     precision: str = "fp32"       # 'fp32' (TF32 off, parity mode) | 'bf16'
     rot_on_cpu: bool = True       # reference behaviour at test time
+    nocsmap_encoder: str = "conv" # 'conv' (MAPEncoder, DCNv3) | 'att' (MAPTransformerEncoer) -- FLAGS.nocsmap_encoder
     h2d_chunk_rois: int = 256     # host inputs: RoI crops are uploaded in chunks of this many RoIs on a copy stream while the
                                   # backbone runs on the previous chunk (0 = one blocking upload like the reference)
 
@@ -84,7 +85,14 @@ def _lin(x, lin: nn.Linear):
     """Linear on channel-last rows; inference uses the cached weight copy in the activation dtype."""
     if not _fused(x):
         return lin(x)
-    return F.linear(x, _cached(lin.weight, x.dtype), _cached(lin.bias, x.dtype))
+    return F.linear(x, _cached(lin.weight, x.dtype), None if lin.bias is None else _cached(lin.bias, x.dtype))
+
+
+def _ln(x, ln: nn.LayerNorm):
+    """LayerNorm over the last dimension; inference uses cached parameter copies in the activation dtype."""
+    if not _fused(x):
+        return ln(x)
+    return F.layer_norm(x, ln.normalized_shape, _cached(ln.weight, x.dtype), _cached(ln.bias, x.dtype), ln.eps)
 
 
 def _conv1x1_rows(x, conv: nn.Conv2d):
@@ -246,7 +254,9 @@ def _gn_act_nhwc(x, gn: nn.GroupNorm, act: str, upsample2x=False):
     y = F.group_norm(x.permute(0, 3, 1, 2), gn.num_groups, gn.weight, gn.bias, gn.eps)
     y = F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
     if upsample2x:
-        y = F.interpolate(y, scale_factor=2, mode="bilinear", align_corners=True)
+        # torch's bilinear kernel on a channels_last-strided fp32 tensor is pathologically slow (4 ms per call at 48 RoIs,
+        # 28 % of the training step); on NCHW-contiguous memory it is a 0.1 ms kernel
+        y = F.interpolate(y.contiguous(), scale_factor=2, mode="bilinear", align_corners=True).contiguous(memory_format=torch.channels_last)
     return y.permute(0, 2, 3, 1)
 
 
@@ -291,6 +301,91 @@ class MAPEncoder(nn.Module):
 
     def forward(self, coor_feat=None, mask_attention=None, cat_id=None, sp2d=None):
         return self.forward_nhwc(coor_feat.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+class _Attention(nn.Module):
+    """timm 0.9.6 ``vision_transformer.Attention`` at ``Block``'s defaults (``qkv_bias=False``, no q/k norm, no dropout)."""
+
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads, self.head_dim = num_heads, dim // num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = _lin(x, self.qkv)
+        if _fused(x) and N == 64 and self.head_dim == 32 and x.is_cuda:
+            o = ops.mhsa_tokens(qkv.contiguous(), self.num_heads)
+        else:
+            q, k, v = qkv.reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4).unbind(0)
+            a = ((q * self.head_dim ** -0.5) @ k.transpose(-2, -1)).softmax(dim=-1)
+            o = (a @ v).transpose(1, 2).reshape(B, N, C)
+        return _lin(o, self.proj)
+
+
+class _Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return _lin(F.gelu(_lin(x, self.fc1)), self.fc2)
+
+
+class ViTBlock(nn.Module):
+    """timm 0.9.6 ``vision_transformer.Block(dim, num_heads)`` as ``attention_pnp_net.py:141`` builds it: pre-norm attention
+    and MLP (ratio 4, exact GELU) with residuals; ``nn.LayerNorm`` default eps 1e-5; LayerScale / DropPath are identities."""
+
+    def __init__(self, dim, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1, self.attn = nn.LayerNorm(dim), _Attention(dim, num_heads)
+        self.norm2, self.mlp = nn.LayerNorm(dim), _Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(_ln(x, self.norm1))
+        return x + self.mlp(_ln(x, self.norm2))
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch_size, in_chans, embed_dim):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+
+class MAPTransformerEncoer(nn.Module):
+    """``attention_pnp_net.py:126-157`` (sic), the ``--nocsmap_encoder=att`` alternative to ``MAPEncoder``: 8x8 patch embedding
+    of the 64x64x3 NOCS map -> + pos_embed -> 3 ViT blocks (dim 256, 8 heads) -> LayerNorm -> (B, 256, 8, 8).
+    State-dict keys follow the reference / timm (``patch_embed.proj``, ``pos_embed``, ``block.i.{norm1,attn.qkv,attn.proj,norm2,
+    mlp.fc1,mlp.fc2}``, ``norm``).  Attention over the 64 tokens runs in ``ops.mhsa_tokens`` at inference."""
+
+    def __init__(self, img_size=64, patch_size=8, in_chans=3, embed_dim=256, depth=3, num_heads=8):
+        super().__init__()
+        self.embed_dim, self.patch, self.grid = embed_dim, patch_size, img_size // patch_size
+        self.norm = nn.LayerNorm(embed_dim)
+        self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)
+        self.pos_embed = nn.Parameter(torch.zeros(1, self.grid * self.grid, embed_dim))
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        self.block = nn.ModuleList([ViTBlock(embed_dim, num_heads) for _ in range(depth)])
+
+    def forward_nhwc(self, x):
+        """x: (B, 64, 64, 3) channel-last -> (B, 8, 8, 256) channel-last (token order = patch raster order)."""
+        B, H, W, Cin = x.shape
+        p, g = self.patch, self.grid
+        # a stride = kernel convolution is a Linear over the flattened patch, in the weight's (c, ky, kx) order
+        patches = x.reshape(B, g, p, g, p, Cin).permute(0, 1, 3, 5, 2, 4).reshape(B, g * g, Cin * p * p)
+        conv = self.patch_embed.proj
+        if _fused(x):
+            t = F.linear(patches, _cached(conv.weight, x.dtype, lambda w: w.flatten(1), "rows"), _cached(conv.bias, x.dtype))
+            t = t + _cached(self.pos_embed, x.dtype)
+        else:
+            t = F.linear(patches, conv.weight.flatten(1), conv.bias) + self.pos_embed
+        for blk in self.block:
+            t = blk(t)
+        return _ln(t, self.norm).reshape(B, g, g, self.embed_dim)
+
+    def forward(self, x):
+        return self.forward_nhwc(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -582,7 +677,12 @@ class PoseNet(nn.Module):
         self.backbone = backbone if backbone is not None else ResNet34Backbone(feature_channel)
         self.xyz_nocs_head = TopDownXyzHead(in_dim=feature_channel, xyz_num_classes=1)
         self.size_head = SizeHead(feature_channel, self.cfg.size_head_out_dim, self.cfg.feat_ts)
-        self.nocs_encoder = MAPEncoder(3, featdim=256)
+        if self.cfg.nocsmap_encoder == "conv":   # PoseNet.py:152-157
+            self.nocs_encoder = MAPEncoder(3, featdim=256)
+        elif self.cfg.nocsmap_encoder == "att":
+            self.nocs_encoder = MAPTransformerEncoer()
+        else:
+            raise NotImplementedError(self.cfg.nocsmap_encoder)
         self.feat_reducer = nn.Conv2d(feature_channel, 256, kernel_size=1)
         self.xyz_deform_head = TopDownXyzHead(in_dim=512, xyz_num_classes=1)
         self.pnp_net = ConvPnPNet(5, featdim=128, rot_dim=4 if "quat" in self.cfg.r_type else 6)
@@ -595,10 +695,11 @@ class PoseNet(nn.Module):
     def _precision(self):
         """fp32: TF32 off (the 1e-4 parity mode).  bf16: inference runs on cached bf16 weight copies with bf16 activations
         (no autocast re-casting); under autograd (training step) it is autocast over the fp32 master weights."""
-        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+        old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic)
         if self.cfg.precision == "fp32":
             torch.backends.cudnn.allow_tf32 = False
             torch.backends.cuda.matmul.allow_tf32 = False
+            torch.backends.cudnn.deterministic = True   # parity mode: no split-K / atomic convolution algorithms
         try:
             if self.cfg.precision == "bf16" and torch.is_grad_enabled():
                 with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -606,7 +707,7 @@ class PoseNet(nn.Module):
             else:
                 yield
         finally:
-            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+            torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.deterministic = old
 
     def _backbone_pipelined(self, img_h, late, dev, dtype):
         """Host-resident RoI crops (the reference uploads them inside ``forward`` too, PoseNet.py:174): chunks of

@@ -148,18 +148,25 @@ int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *
                                 void *out, int N, int H, int W, int K, int C, long long rows, float eps, int dtype, void *stream);
 
 /* y = act(GroupNorm_G(x)) on channel-last (N,H,W,C) activations (layer_utils.py:32-60 "GN", conv_module.py order
- * conv -> norm -> act); act: 0 none, 1 ReLU, 2 exact GELU.  stats: N*G*2 floats of scratch (zeroed by the call). */
-int gp_groupnorm_act(const void *x, void *y, float *stats, const float *gamma, const float *beta, int N, int H, int W,
-                     int C, int G, float eps, int act, int dtype, void *stream);
+ * conv -> norm -> act); act: 0 none, 1 ReLU, 2 GELU.  stats: scratch of at least gp_groupnorm_workspace_floats(N,H,W,G)
+ * floats (no need to clear it).  Sums are taken in a fixed order (no atomics): results are bit-reproducible. */
+size_t gp_groupnorm_workspace_floats(int N, int H, int W, int G);
+int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N,
+                     int H, int W, int C, int G, float eps, int act, int dtype, void *stream);
 
 /* y = Conv1x1_{C->OC}(act(GroupNorm_G(x))) + bias: the decoder's last ConvModule norm/activation fused with its
  * out_layer (xyz_head.py:349-366, Conv1x1 256 -> 3); the normalised C-channel activation is never written.
  * x (N,H,W,C) channel-last, y (N,H,W,OC) of `dtype`; w [OC][C] and bias [OC] fp32.  Supported: C == 256, OC == 3.
  * For 16-bit storage GELU is evaluated with a tanh-form fit of the erf GELU (error < 2.5e-4 |x|, below the bf16
  * rounding of the result); fp32 keeps the erf form (abs error 1.5e-7).  The same holds for gp_groupnorm_act. */
-int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, const float *gamma, const float *beta, const float *w,
-                             const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC, int dtype,
-                             void *stream);
+int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                             const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                             int dtype, void *stream);
+
+/* Multi-head self-attention over the 64 patch tokens of MAPTransformerEncoer (attention_pnp_net.py:126-157, the
+ * `--nocsmap_encoder=att` alternative to MAPEncoder; timm 0.9.6 Attention.forward): out = softmax(q k^T * scale) v per head.
+ * qkv (B, NT, 3, NH, HD) as the qkv Linear emits it, out (B, NT, NH*HD), both of `dtype`.  Supported: NT == 64, HD == 32. */
+int gp_mhsa_tokens(const void *qkv, void *out, int B, int NT, int NH, int HD, float scale, int dtype, void *stream);
 
 /* Operand packing for a 7x7 / stride-2 / pad-3 stem convolution over 3 input channels (network/resnet.py:104, the
  * stand-in backbone of the synthetic runs) evaluated as a 4x4 / stride-1 convolution over the 2x2 space-to-depth image:

@@ -286,15 +286,81 @@ def pose_from_predictions_train(rots, centroids, z_vals, cams, centers, resize_r
 
 
 # ------------------------------------------------------------------------------------------------------
+# MAPTransformerEncoer (attention_pnp_net.py:126-157, `--nocsmap_encoder=att`).  PARITY UNPINNED: its blocks are
+# `timm.models.vision_transformer.Block` (timm==0.9.6, GIVEPose_env.yml), a third-party dependency that is neither vendored
+# under /root/reference nor installed here, so the reference cannot be run for this branch.  Restated from timm 0.9.6's
+# published source: Block(dim, num_heads) = x + proj(softmax(q k^T hd^-0.5) v) on LayerNorm(x) [qkv_bias=False, eps 1e-5],
+# then x + fc2(GELU(fc1(LayerNorm(x)))) with hidden = 4 dim; LayerScale / DropPath are identities at the defaults.
+# ------------------------------------------------------------------------------------------------------
+class _OAttention(nn.Module):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads, self.scale = num_heads, (dim // num_heads) ** -0.5
+        self.qkv, self.proj = nn.Linear(dim, dim * 3, bias=False), nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        q, k, v = qkv.unbind(0)
+        attn = ((q * self.scale) @ k.transpose(-2, -1)).softmax(dim=-1)
+        return self.proj((attn @ v).transpose(1, 2).reshape(B, N, C))
+
+
+class _OMlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.fc2 = nn.Linear(dim, hidden), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(F.gelu(self.fc1(x)))
+
+
+class _OBlock(nn.Module):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.norm1, self.attn, self.norm2, self.mlp = nn.LayerNorm(dim), _OAttention(dim, num_heads), nn.LayerNorm(dim), _OMlp(dim, 4 * dim)
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class _OPatchEmbed(nn.Module):
+    def __init__(self, patch, cin, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(cin, dim, patch, patch)
+
+    def forward(self, x):   # attention_pnp_net.py:296-303
+        return self.proj(x).flatten(2).transpose(1, 2)
+
+
+class MAPTransformerEncoer(nn.Module):
+    def __init__(self, img_size=64, patch_size=8, in_chans=3, embed_dim=256, depth=3, num_heads=8):
+        super().__init__()
+        self.embed_dim = embed_dim
+        self.norm = nn.LayerNorm(embed_dim)
+        self.patch_embed = _OPatchEmbed(patch_size, in_chans, embed_dim)
+        self.pos_embed = nn.Parameter(torch.zeros(1, (img_size // patch_size) ** 2, embed_dim))
+        self.block = nn.ModuleList([_OBlock(embed_dim, num_heads) for _ in range(depth)])
+
+    def forward(self, x):   # :143-157
+        x = self.patch_embed(x) + self.pos_embed
+        for blk in self.block:
+            x = blk(x)
+        x = self.norm(x).permute(0, 2, 1)
+        return x.reshape(x.shape[0], self.embed_dim, 8, 8)
+
+
+# ------------------------------------------------------------------------------------------------------
 # the model
 # ------------------------------------------------------------------------------------------------------
 class PoseNet(nn.Module):
-    def __init__(self):
+    def __init__(self, nocsmap_encoder="conv"):
         super().__init__()
         self.backbone = Backbone()
         self.xyz_nocs_head = TopDownXyzHead(1024)
         self.size_head = SizeHead(1024)
-        self.nocs_encoder = MAPEncoder(3, 256)
+        self.nocs_encoder = MAPEncoder(3, 256) if nocsmap_encoder == "conv" else MAPTransformerEncoer()   # PoseNet.py:152-157
         self.feat_reducer = nn.Conv2d(1024, 256, 1)
         self.xyz_deform_head = TopDownXyzHead(512)
         self.pnp_net = ConvPnPNet(5, 128)
@@ -347,6 +413,9 @@ def init_weights(net: nn.Module, mode: str, seed: int = 0) -> None:
             for m in net.modules():
                 if isinstance(m, DCNv3) or type(m).__name__ == "DCNv3":
                     m.offset.weight.mul_(2.0)
+        for name, p in net.named_parameters():   # MAPTransformerEncoer: trunc_normal_(pos_embed, std=.02) (attention_pnp_net.py:139)
+            if name.endswith("pos_embed"):
+                p.copy_((torch.randn(p.shape, generator=g) * 0.02).clamp_(-2.0, 2.0))
 
 
 def make_inputs(B: int, seed: int = 0) -> dict:
