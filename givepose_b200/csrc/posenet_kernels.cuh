@@ -161,19 +161,27 @@ small_k_linear_kernel(const T *__restrict__ x /*(rows,K)*/, const float *__restr
         for (int j = 0; j < V; ++j) wr[k][j] = __ldg(w + k * C + V * cq + j);
 #pragma unroll
     for (int j = 0; j < V; ++j) b[j] = __ldg(bias + V * cq + j);
-    for (long long r = (long long)blockIdx.x * pstep + prow; r < rows; r += (long long)gridDim.x * pstep) {
-        float xv[K];
+    constexpr int U = 4;   // rows in flight per thread: the kernel is a pure 16-byte store stream
+    const long long stride = (long long)gridDim.x * pstep;
+    for (long long r0 = (long long)blockIdx.x * pstep + prow; r0 < rows; r0 += U * stride) {
+        float xv[U][K];
 #pragma unroll
-        for (int k = 0; k < K; ++k) xv[k] = to_acc<T>(x[r * K + k]);
-        float o[V];
+        for (int u = 0; u < U; ++u)
 #pragma unroll
-        for (int j = 0; j < V; ++j) {
-            float a = b[j];
+            for (int k = 0; k < K; ++k) xv[u][k] = r0 + u * stride < rows ? to_acc<T>(x[(r0 + u * stride) * K + k]) : 0.f;
 #pragma unroll
-            for (int k = 0; k < K; ++k) a = fmaf(xv[k], wr[k][j], a);
-            o[j] = a;
+        for (int u = 0; u < U; ++u) {
+            if (r0 + u * stride >= rows) break;
+            float o[V];
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                float a = b[j];
+#pragma unroll
+                for (int k = 0; k < K; ++k) a = fmaf(xv[u][k], wr[k][j], a);
+                o[j] = a;
+            }
+            Vec<T, V>::store_stream(out + (r0 + u * stride) * C + V * cq, o);
         }
-        Vec<T, V>::store_stream(out + r * C + V * cq, o);
     }
 }
 

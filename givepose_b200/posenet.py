@@ -254,9 +254,10 @@ def _gn_act_nhwc(x, gn: nn.GroupNorm, act: str, upsample2x=False):
     y = F.group_norm(x.permute(0, 3, 1, 2), gn.num_groups, gn.weight, gn.bias, gn.eps)
     y = F.relu(y) if act == "relu" else F.gelu(y) if act == "gelu" else y
     if upsample2x:
-        # torch's bilinear kernel on a channels_last-strided fp32 tensor is pathologically slow (4 ms per call at 48 RoIs,
-        # 28 % of the training step); on NCHW-contiguous memory it is a 0.1 ms kernel
-        y = F.interpolate(y.contiguous(), scale_factor=2, mode="bilinear", align_corners=True).contiguous(memory_format=torch.channels_last)
+        # group_norm hands back NCHW-contiguous memory, and torch's NCHW bilinear kernel parallelises over the H*W output
+        # pixels only (4 ms per call at 48 RoIs x 256 channels, 28 % of the training step); its channels_last kernel covers
+        # every element
+        y = F.interpolate(y.contiguous(memory_format=torch.channels_last), scale_factor=2, mode="bilinear", align_corners=True)
     return y.permute(0, 2, 3, 1)
 
 
