@@ -1,0 +1,359 @@
+// givepose_b200 -- dense layers of the PoseNet heads on the 5th-generation tensor cores (sm_100a):
+//
+//     y[M,N] = act(x[M,K] . w[N,K]^T + bias[N])          bf16 operands, fp32 accumulation in TMEM, bf16 result
+//
+// This is the shape of every Linear / 1x1 convolution on the path -- DCNv3's input_proj / output_proj / offset / mask
+// (modules/dcnv3.py:325-354, K = 256), feat_reducer (PoseNet.py:158), and the PnP regression trunk fc1||fc1_z, fc2, fc2_z
+// (conv_pnp_net.py:172-199, K = 8192 / 1024) with its LeakyReLU(0.1) -- with the bias and the activation applied in the
+// epilogue instead of in separate elementwise passes.
+//
+// Structure: persistent CTAs (one per SM, 192 threads, warp-specialised) walking the 128 x BN output tiles, n fastest so the
+// CTAs that share a slab of x run together (the second read hits L2):
+//   warp 0     TMA producer: cp.async.bulk.tensor.2d loads of a 128 x 64 slab of x and a BN x 64 slab of w per K step into a
+//              ring of 128B-swizzled shared-memory stages, completion signalled on mbarriers (expect_tx); runs ahead across
+//              tile boundaries
+//   warp 1     allocates 2 x BN TMEM columns (two accumulators); one elected thread issues
+//              tcgen05.mma.cta_group::1.kind::f16 (M128 x BN x K16, both operands K-major from shared memory through 64-bit
+//              matrix descriptors); tcgen05.commit releases each stage back to the producer and hands the finished
+//              accumulator to the epilogue
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns at a time (warp w owns TMEM lanes 32*(w%4)..+31 = output rows),
+//              + bias, activation, pack to bf16 into a swizzled staging tile, release the accumulator (so the MMAs of the tile
+//              after next start while this one is written out), then row-contiguous 16-byte global stores
+// Rows / columns beyond M / N and the K tail are zero-filled by TMA on the way in and masked on the way out.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "givepose_b200.h"
+
+namespace gp {
+extern unsigned long long g_launches;
+
+namespace tc {
+
+constexpr int BM = 128, BK = 64;                   // CTA tile rows; BK bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;                         // K per tcgen05.mma for 16-bit operands
+constexpr int THREADS = 192;
+constexpr int A_BYTES = BM * BK * 2;
+
+template <int BN> struct Cfg {
+    static constexpr int B_BYTES = BN * BK * 2, STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = BN == 128 ? 4 : 3;
+    static constexpr int OUT_BYTES = BM * BN * 2;              // staging tile of the epilogue (32 rows x BN per warp)
+    static constexpr int TMEM_COLS = 2 * BN;                   // two fp32 accumulators of 128 lanes x BN columns
+    static constexpr int BIAS_BYTES = 4 * BN * 4;               // one fp32 copy of the tile's bias slice per epilogue warp
+    static constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + OUT_BYTES + BIAS_BYTES + 256 /*barriers*/;
+    // instruction descriptor, kind::f16: D fp32 (bit 4), A/B bf16 (bits 7, 10), both K-major, N >> 3 at [17,23), M >> 4 at [24,29)
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+};
+
+enum : int { ACT_NONE = 0, ACT_LRELU = 1, ACT_RELU = 2 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// 64-bit shared-memory matrix descriptor, K-major operand in a 128B-swizzled tile (rows of 128 bytes, 8-row atoms of
+// 1024 bytes): start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 1024 >> 4, version 1 (Blackwell),
+// layout type 2 = SWIZZLE_128B.  (Field layout: PTX ISA "tcgen05 matrix descriptor"; CUTLASS cute/arch/mma_sm100_desc.hpp.)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {   // arrives on `bar` once all MMAs issued so far have completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int ACT> __device__ __forceinline__ float activate(float v, float slope) {
+    if (ACT == ACT_LRELU) return fmaxf(v, v * slope);   // 0 <= slope <= 1 (checked on the host)
+    if (ACT == ACT_RELU) return fmaxf(v, 0.f);
+    return v;
+}
+
+template <int BN, int ACT>
+__global__ void __launch_bounds__(THREADS, 1)
+linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                   const float *__restrict__ bias, __nv_bfloat16 *__restrict__ y, int M, int N, int K, float slope) {
+    using C = Cfg<BN>;
+    constexpr int STAGES = C::STAGES, STAGE_BYTES = C::STAGE_BYTES;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
+    const uint32_t out_stage = base + STAGES * STAGE_BYTES;
+    const uint32_t bias_stage = out_stage + C::OUT_BYTES;
+    const uint32_t bars = bias_stage + C::BIAS_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * STAGES + a); };
+    auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * STAGES + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 4);         // 4 bytes: TMEM base address written by tcgen05.alloc
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));      // generic pointer to the aligned base
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_blocks = (N + BN - 1) / BN, m_blocks = (M + BM - 1) / BM;
+    const long long tiles = (long long)n_blocks * m_blocks;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 4);   // one arrival per epilogue warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {   // one warp allocates (and later frees) the accumulator columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)C::TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;   // K steps issued so far, across tiles
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+                const int m0 = (int)(tile / n_blocks) * BM, n0 = (int)(tile % n_blocks) * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);               // slot free (passes immediately on the first lap)
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    tma_load_2d(base + s * STAGE_BYTES, &map_x, full_bar(s), kb * BK, m0);
+                    tma_load_2d(base + s * STAGE_BYTES + A_BYTES, &map_w, full_bar(s), kb * BK, n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, lt = 0;   // K steps / tiles consumed so far
+            for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+                const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+                mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);        // epilogue has drained this accumulator (first two pass)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);                      // TMA landed this stage
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = base + s * STAGE_BYTES, b_addr = a_addr + A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        // advancing 16 bf16 = 32 bytes along K inside the swizzle row: +2 in the (>> 4) start-address field
+                        umma_bf16(tmem_d, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), C::IDESC, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));                       // stage reusable once these MMAs have read it
+                }
+                umma_commit(tmem_full_bar(acc));                     // accumulator complete
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        // TMEM row -> registers -> bias / activation -> bf16 -> this warp's 32-row staging tile (16-byte chunks XOR-swizzled by
+        // the row so both the row-per-lane writes and the row-major reads are conflict-free) -> global stores in which the
+        // warp covers whole output rows.
+        const int q = warp & 3;
+        constexpr int ROW_BYTES = BN * 2, CHUNKS = BN / 8;   // 16-byte chunks per staged row
+        uint8_t *stage = smem_gen + (out_stage - base) + q * (32 * ROW_BYTES);
+        float *s_bias = reinterpret_cast<float *>(smem_gen + (bias_stage - base)) + q * BN;
+        const bool vec_ok = (N % 8) == 0;
+        uint32_t lt = 0;
+        for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++lt) {
+            const int m0 = (int)(tile / n_blocks) * BM, n0 = (int)(tile % n_blocks) * BN;
+            const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+            // this warp's copy of the tile's bias slice (overlaps the wait for the accumulator)
+#pragma unroll
+            for (int j = lane; j < BN; j += 32) s_bias[j] = n0 + j < N ? __ldg(bias + n0 + j) : 0.f;
+            __syncwarp();
+            mbar_wait(tmem_full_bar(acc), acc_ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c;
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    const float4 b0 = *reinterpret_cast<const float4 *>(s_bias + c + j), b1 = *reinterpret_cast<const float4 *>(s_bias + c + j + 4);
+                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a = activate<ACT>(__uint_as_float(r[j + 2 * t]) + bv[2 * t], slope);
+                        const float b = activate<ACT>(__uint_as_float(r[j + 2 * t + 1]) + bv[2 * t + 1], slope);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        pk[t] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    const int chunk = (c + j) >> 3;
+                    *reinterpret_cast<uint4 *>(stage + lane * ROW_BYTES + ((chunk ^ (lane & (CHUNKS - 1))) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                }
+            }
+            // every TMEM read of this accumulator has completed: hand it back before writing the tile out
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+            constexpr int ROWS_PER_IT = 32 / CHUNKS;   // rows covered by one warp-wide 16-byte store (2 for BN 128, 1 for 256)
+            const int chunk = lane % CHUNKS, col = n0 + chunk * 8, rsub = lane / CHUNKS;
+            const int rows_here = min(32, M - (m0 + q * 32));   // may be <= 0
+            if (vec_ok && col + 8 <= N) {
+#pragma unroll 4
+                for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+                    const int rl = ROWS_PER_IT * it + rsub;
+                    if (rl < rows_here) {
+                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + rl * ROW_BYTES + ((chunk ^ (rl & (CHUNKS - 1))) << 4));
+                        *reinterpret_cast<uint4 *>(y + (size_t)(m0 + q * 32 + rl) * N + col) = v;
+                    }
+                }
+            } else if (col < N) {
+                for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+                    const int rl = ROWS_PER_IT * it + rsub;
+                    if (rl >= rows_here) break;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + rl * ROW_BYTES + ((chunk ^ (rl & (CHUNKS - 1))) << 4));
+                    const __nv_bfloat16 *e = reinterpret_cast<const __nv_bfloat16 *>(&v);
+                    __nv_bfloat16 *dst = y + (size_t)(m0 + q * 32 + rl) * N + col;
+                    for (int t = 0; t < 8 && col + t < N; ++t) dst[t] = e[t];
+                }
+            }
+            __syncwarp();   // the staging and bias tiles are rewritten by the next tile
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)C::TMEM_COLS) : "memory");
+    }
+}
+
+// ---- host side: tensor maps through the driver entry point (no link-time dependency on libcuda) -----------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+// row-major [rows, K] bf16 matrix, box = BK x box_rows, 128-byte swizzle, out-of-bounds reads return zero
+static bool make_map(CUtensorMap *map, const void *ptr, int rows, int K, int box_rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace tc
+}  // namespace gp
+
+template <int BN, int ACT>
+static int launch_linear(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, float slope, cudaStream_t st) {
+    using namespace gp::tc;
+    using C = Cfg<BN>;
+    static bool attr_set = false;
+    static int sms = 0;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    CUtensorMap mx, mw;
+    if (!make_map(&mx, x, M, K, BM) || !make_map(&mw, w, N, K, BN)) return GP_ERR_UNSUPPORTED;
+    const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);   // persistent: one CTA per SM
+    linear_bf16_kernel<BN, ACT><<<grid, THREADS, C::SMEM_BYTES, st>>>(mx, mw, bias, (__nv_bfloat16 *)y, M, N, K, slope);
+    gp::g_launches += 1;
+    return (int)cudaGetLastError();
+}
+
+template <int BN>
+static int launch_linear_act(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
+                             cudaStream_t st) {
+    using namespace gp::tc;
+    if (act == ACT_LRELU) return launch_linear<BN, ACT_LRELU>(x, w, bias, y, M, N, K, slope, st);
+    if (act == ACT_RELU) return launch_linear<BN, ACT_RELU>(x, w, bias, y, M, N, K, slope, st);
+    return launch_linear<BN, ACT_NONE>(x, w, bias, y, M, N, K, slope, st);
+}
+
+extern "C" int gp_linear_bf16(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
+                              void *stream) {
+    if (!x || !w || !bias || !y) return GP_ERR_NULL;
+    if (M < 0 || N <= 0 || K <= 0 || K % 8) return GP_ERR_SHAPE;   // 16-byte row pitch for the tensor maps
+    if (act < 0 || act > 2 || (act == 1 && !(slope >= 0.f && slope <= 1.f))) return GP_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
+    if (M == 0) return GP_OK;
+    // 128 x 256 tiles when there are enough of them to fill the machine: x is read once per 256 output columns, and a
+    // K16 step reads 12 KB of operands per 128 tensor-pipe cycles instead of 8 KB per 64 (shared-memory bound at N = 128)
+    const long long tiles256 = (long long)((N + 255) / 256) * ((M + 127) / 128);
+    if (N > 128 && tiles256 >= 148) return launch_linear_act<256>(x, w, bias, y, M, N, K, act, slope, (cudaStream_t)stream);
+    return launch_linear_act<128>(x, w, bias, y, M, N, K, act, slope, (cudaStream_t)stream);
+}

@@ -127,6 +127,27 @@ def groupnorm_act_conv1x1(x, gamma, beta, weight, bias, groups=32, eps=1e-5, act
     return y
 
 
+LIN_ACT = {"none": 0, "lrelu": 1, "relu": 2}
+
+
+def linear_bf16(x, weight, bias=None, act="none", slope=0.1):
+    """``act(x @ weight.T + bias)`` on the tcgen05 tensor cores: ``x`` (..., K) and ``weight`` (N, K) bf16, ``bias`` fp32 (N,) or
+    None; returns (..., N) bf16.  ``act``: 'none' | 'lrelu' (``slope``) | 'relu'."""
+    _need_cuda("input", x, torch.bfloat16)
+    _need_cuda("weight", weight, torch.bfloat16)
+    N, K = weight.shape
+    if x.shape[-1] != K or K % 8:
+        raise RuntimeError(f"linear_bf16: unsupported shapes {tuple(x.shape)} x {tuple(weight.shape)}")
+    if bias is None:
+        bias = torch.zeros(N, dtype=torch.float32, device=x.device)
+    _need_cuda("bias", bias, torch.float32)
+    M = x.numel() // K
+    y = torch.empty((*x.shape[:-1], N), dtype=torch.bfloat16, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_linear_bf16(_vp(x), _vp(weight), _vp(bias), _vp(y), M, N, K, LIN_ACT[act], float(slope), _stream(x)), "linear_bf16")
+    return y
+
+
 def mhsa_tokens(qkv, num_heads):
     """Self-attention over the 64 patch tokens of ``MAPTransformerEncoer``: ``qkv`` (B, 64, 3*C) straight from the qkv
     Linear (timm layout ``(B, N, 3, heads, C/heads)``) -> (B, 64, C)."""

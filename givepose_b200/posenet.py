@@ -53,6 +53,8 @@ class PoseNetConfig:
     precision: str = "fp32"       # 'fp32' (TF32 off, parity mode) | 'bf16'
     rot_on_cpu: bool = True       # reference behaviour at test time
     nocsmap_encoder: str = "conv" # 'conv' (MAPEncoder, DCNv3) | 'att' (MAPTransformerEncoer) -- FLAGS.nocsmap_encoder
+    tc_linear: bool = True        # bf16 inference: PnP regression trunk (fc1||fc1_z, fc2, fc2_z + LeakyReLU) on the hand-written
+                                  # tcgen05 dense layer (ops.linear_bf16) instead of cuBLAS + separate activation kernels
     h2d_chunk_rois: int = 256     # host inputs: RoI crops are uploaded in chunks of this many RoIs on a copy stream while the
                                   # backbone runs on the previous chunk (0 = one blocking upload like the reference)
 
@@ -470,6 +472,7 @@ class ConvPnPNet(nn.Module):
         self.fc1, self.fc2 = nn.Linear(featdim * 64, 1024), nn.Linear(1024, 256)
         self.fc1_z, self.fc2_z = nn.Linear(featdim * 64, 1024), nn.Linear(1024, 256)
         self.fc_z, self.fc_r, self.fc_t = nn.Linear(256, 1), nn.Linear(256, rot_dim), nn.Linear(256, 2)
+        self.tc_linear = True
         for m in self.modules():   # :124-134
             if isinstance(m, (nn.Conv2d, nn.Linear)):
                 nn.init.normal_(m.weight, std=0.001)
@@ -496,16 +499,25 @@ class ConvPnPNet(nn.Module):
         pnp_feat = x.permute(0, 3, 1, 2)
         flat = pnp_feat.reshape(x.shape[0], -1)   # NCHW flatten order (conv_pnp_net.py:168-170): checkpoint compatible
         # fc1 || fc1_z read the same 8192-wide activation: one GEMM over the concatenated weights
+        tc = _fused(x) and self.tc_linear and flat.dtype == torch.bfloat16 and flat.is_cuda
         if _fused(x):
             vers = (self.fc1.weight._version, self.fc1_z.weight._version, self.fc1.bias._version, self.fc1_z.bias._version, flat.dtype, flat.device)
             if getattr(self, "_fc1_cat", (None,))[0] != vers:
+                bcat = torch.cat([self.fc1.bias, self.fc1_z.bias]).detach()
                 self._fc1_cat = (vers, torch.cat([self.fc1.weight, self.fc1_z.weight]).detach().to(flat.dtype).contiguous(),
-                                 torch.cat([self.fc1.bias, self.fc1_z.bias]).detach().to(flat.dtype).contiguous())
-            h = F.leaky_relu(F.linear(flat, self._fc1_cat[1], self._fc1_cat[2]), 0.1)
+                                 bcat.to(flat.dtype).contiguous(), bcat.float().contiguous())
+            if tc:   # tcgen05 GEMM, bias + LeakyReLU(0.1) in its epilogue (conv_pnp_net.py:172-199)
+                h = ops.linear_bf16(flat.contiguous(), self._fc1_cat[1], self._fc1_cat[3], "lrelu", 0.1)
+            else:
+                h = F.leaky_relu(F.linear(flat, self._fc1_cat[1], self._fc1_cat[2]), 0.1)
         else:
             h = F.leaky_relu(F.linear(flat, torch.cat([self.fc1.weight, self.fc1_z.weight]), torch.cat([self.fc1.bias, self.fc1_z.bias])), 0.1)
-        hr = F.leaky_relu(_lin(h[:, :1024], self.fc2), 0.1)
-        hz = F.leaky_relu(_lin(h[:, 1024:], self.fc2_z), 0.1)
+        if tc:
+            hr = ops.linear_bf16(h[:, :1024].contiguous(), _cached(self.fc2.weight, torch.bfloat16), _cached(self.fc2.bias, torch.float32), "lrelu", 0.1)
+            hz = ops.linear_bf16(h[:, 1024:].contiguous(), _cached(self.fc2_z.weight, torch.bfloat16), _cached(self.fc2_z.bias, torch.float32), "lrelu", 0.1)
+        else:
+            hr = F.leaky_relu(_lin(h[:, :1024], self.fc2), 0.1)
+            hz = F.leaky_relu(_lin(h[:, 1024:], self.fc2_z), 0.1)
         rot = _lin(hr, self.fc_r)
         t = torch.cat([_lin(hr, self.fc_t), _lin(hz, self.fc_z)], dim=1)
         return rot, t, pnp_feat
@@ -687,6 +699,7 @@ class PoseNet(nn.Module):
         self.feat_reducer = nn.Conv2d(feature_channel, 256, kernel_size=1)
         self.xyz_deform_head = TopDownXyzHead(in_dim=512, xyz_num_classes=1)
         self.pnp_net = ConvPnPNet(5, featdim=128, rot_dim=4 if "quat" in self.cfg.r_type else 6)
+        self.pnp_net.tc_linear = self.cfg.tc_linear
         self.out_res, self.ROT_TYPE, self.TRANS_TYPE, self.Z_TYPE = self.cfg.out_res, self.cfg.r_type, "centroid_z", "REL"
         if "rot6d" not in self.cfg.r_type:
             raise NotImplementedError("GIVEPose's config uses r_type='allo_rot6d' (config/config.py)")

@@ -48,7 +48,10 @@ class GradBucket:
         self.flat = torch.zeros(self.numel, dtype=torch.float32, device=self.params[0].device)
         self.views, o = [], 0
         for p in self.params:
-            self.views.append(self.flat[o:o + p.numel()].view_as(p))
+            chunk = self.flat[o:o + p.numel()]
+            # same strides as the parameter (conv weights are kept channels_last): autograd then accumulates without a layout copy
+            dense = p.is_contiguous() or p.is_contiguous(memory_format=torch.channels_last) if p.dim() == 4 else p.is_contiguous()
+            self.views.append(chunk.as_strided(p.size(), p.stride()) if dense else chunk.view_as(p))
             o += p.numel()
         self.attach()
 

@@ -163,6 +163,14 @@ int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_
                              const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
                              int dtype, void *stream);
 
+/* Dense layer on the tcgen05 tensor cores: y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]), x / w / y bf16 row-major, bias fp32,
+ * fp32 accumulation in TMEM, bias + activation in the epilogue (act: 0 none, 1 LeakyReLU(slope), 2 ReLU).  The shape of
+ * every Linear / 1x1 convolution of the heads: DCNv3 input_proj / output_proj / offset / mask (modules/dcnv3.py:325-354),
+ * feat_reducer (PoseNet.py:158), fc1||fc1_z, fc2, fc2_z with their LeakyReLU(0.1) (conv_pnp_net.py:172-199).
+ * K % 8 == 0 (16-byte row pitch); any M, N (tails are masked).  TMA operand loads, 3-stage mbarrier ring, two CTAs per SM. */
+int gp_linear_bf16(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
+                   void *stream);
+
 /* Multi-head self-attention over the 64 patch tokens of MAPTransformerEncoer (attention_pnp_net.py:126-157, the
  * `--nocsmap_encoder=att` alternative to MAPEncoder; timm 0.9.6 Attention.forward): out = softmax(q k^T * scale) v per head.
  * qkv (B, NT, 3, NH, HD) as the qkv Linear emits it, out (B, NT, NH*HD), both of `dtype`.  Supported: NT == 64, HD == 32. */

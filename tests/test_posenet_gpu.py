@@ -268,6 +268,23 @@ def test_posenet_bf16_within_stated_tolerance(OP):
     assert ang.median() < 5.0 and (ang < 15.0).sum() >= len(ang) - 1, ang.tolist()
 
 
+def test_pnp_head_on_tcgen05_matches_library_gemms(OP):
+    """PoseNetConfig.tc_linear: the PnP trunk on ``ops.linear_bf16`` (tcgen05, bias + LeakyReLU fused) vs cuBLAS + elementwise."""
+    from givepose_b200.posenet import PoseNet, PoseNetConfig
+    ora = OP.PoseNet().eval()
+    OP.init_weights(ora, "o1", seed=0)
+    data = OP.make_inputs(8, seed=0)
+    outs = []
+    for tc in (True, False):
+        net = PoseNet(PoseNetConfig(precision="bf16", tc_linear=tc)).eval()
+        net.load_state_dict(ora.state_dict(), strict=True)
+        with torch.no_grad():
+            outs.append(net.cuda()(data, "cuda"))
+    assert rel(outs[0]["trans"], outs[1]["trans"]) < 2e-2 and rel(outs[0]["size"], outs[1]["size"]) < 1e-6
+    ang = torch.rad2deg(torch.acos(((torch.einsum("bij,bij->b", outs[0]["rot"].double(), outs[1]["rot"].double()) - 1) / 2).clamp(-1, 1)))
+    assert ang.max() < 3.0, ang.tolist()
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_posenet_inference_is_bit_reproducible(OP, precision):
     """No atomics on the inference path (GroupNorm statistics are summed in a fixed order): two independent runs agree bit for bit."""
