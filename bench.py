@@ -126,6 +126,30 @@ def time_cpu_port(n_sample, steps, warmup, dist):
     return (fwd + bwd) / dt / 1e9, dt, torch.get_num_threads()
 
 
+def time_reference_cuda(inp, off, m, gout, dtype_name, timed, reps, ms_fwd, ms_bwd):
+    """Times the reference's own CUDA kernels (checker artefact, never on the product path) on the bench inputs.
+    The reference dispatches double/float/half only (dcnv3_cuda.cu:69): bf16 runs are compared with its half path."""
+    try:
+        from oracle import build_ref_ext
+        if not os.path.exists(build_ref_ext.OUT):
+            return {"unavailable": "oracle/_ref/DCNv3_ref.so not built"}
+        ref = build_ref_ext.load()
+        rd = torch.float32 if dtype_name == "f32" else torch.float16
+        ri, ro, rm, rg = (t.to(rd) for t in (inp, off, m, gout))
+        for _ in range(2):
+            ref.dcnv3_forward(ri, ro, rm, *ARGS, 256, 0)
+            ref.dcnv3_backward(ri, ro, rm, *ARGS, rg, 256, 0)
+        rf = timed(lambda: ref.dcnv3_forward(ri, ro, rm, *ARGS, 256, 0), reps)
+        rb = timed(lambda: ref.dcnv3_backward(ri, ro, rm, *ARGS, rg, 256, 0), reps)
+        return {"what": "reference ops_dcnv3 CUDA extension compiled unmodified for sm_100a, same GPU, same inputs",
+                "dtype": "f32" if rd == torch.float32 else "f16 (reference has no bf16)", "fwd_ms": round(rf, 4), "bwd_ms": round(rb, 4),
+                "ours_fwd_ms": round(ms_fwd, 4), "ours_bwd_ms": round(ms_bwd, 4),
+                "speedup_fwd": round(rf / ms_fwd, 2), "speedup_bwd": round(rb / ms_bwd, 2),
+                "speedup_fwd_bwd": round((rf + rb) / (ms_fwd + ms_bwd), 2)}
+    except Exception as e:   # the checker must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+
+
 # ---- PoseNet RoIs/s (BASELINE configs[2..3]) ---------------------------------------------------------------
 # per-RoI algorithmic FLOPs (2*MAC, SURVEY.md 8(d) D4): decoders 12.99 + 12.84 G, MAPEncoder 1.40 G, ConvPnPNet 0.14 G,
 # feat_reducer 0.034 G, ResNet-34 trunk @256^2 ~ 7.34 G (+ neck 0.067 G)
@@ -248,17 +272,37 @@ def run_posenet(args, rank, world, dev, dist):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(args.posenet_steps):
+        for _ in range(3):
             loss = train_step(net, tdata, tgt, opt, bucket, dev, criterion=crit)
+        e1.record()
+        barrier()
+        t_eager = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
+        # the same step captured once as a CUDA graph (zero -> fwd -> loss -> bwd -> all-reduce -> clip -> SGD) and replayed
+        from givepose_b200 import _lib
+        from givepose_b200.train import GraphedTrainStep
+        n0 = int(_lib.lib.gp_launch_count())
+        gstep = GraphedTrainStep(net, opt, bucket, dev, tdata, tgt, criterion=crit, warmup=1)
+        ours_per_step = (int(_lib.lib.gp_launch_count()) - n0) // 2   # 1 warm-up + the captured step
+        for _ in range(2):
+            gstep(tdata, tgt)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.posenet_steps):
+            loss = gstep(tdata, tgt)   # refreshes the static input / target buffers (D2D here), then one graph launch
         e1.record()
         barrier()
         t = torch.tensor([e0.elapsed_time(e1) / args.posenet_steps], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t_eager, op=dist.ReduceOp.MAX)
         out["train_step"] = {"value": round(tb * world / (t.item() * 1e-3), 1), "unit": "RoIs/s", "rois_per_gpu": tb, "scaling": "weak",
-                             "ms_per_step": round(t.item(), 3), "dtype": "bf16 autocast, fp32 master weights + grads",
-                             "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum)/world, one flat bucket" if world > 1 else "none (1 rank)",
+                             "ms_per_step": round(t.item(), 3), "mode": "one CUDA graph per step (givepose_b200.train.GraphedTrainStep)",
+                             "eager_ms_per_step": round(t_eager.item(), 3), "our_kernels_per_step": ours_per_step,
+                             "dtype": "bf16 autocast, fp32 master weights + grads",
+                             "allreduce_bytes": bucket.nbytes(), "collective": "nccl all_reduce(sum)/world, one flat bucket, inside the graph" if world > 1 else "none (1 rank)",
                              "loss": "givepose_b200.loss.PoseLoss (reference losses/pose_loss.py terms, batched on device, 1/3 symmetric RoIs)", "last_loss": round(float(loss), 5)}
+        del gstep
         del net, opt, bucket
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -464,6 +508,12 @@ def main():
                "sample": f"oracle.dcnv3.dcnv3_core_torch fwd + autograd bwd, N={n_s} of 64 RoIs, fp32, 1 warm-up + 3 timed, "
                          f"{dt_cpu * 1e3:.1f} ms/step"}
 
+    # the reference's OWN CUDA kernels (oracle/_ref/DCNv3_ref.so, built unmodified by oracle/build_ref_ext.py) on this
+    # same GPU and the same inputs: informational, beside the CPU baseline the contract asks for
+    ref_cuda = None
+    if not args.no_cpu_baseline and world == 1:
+        ref_cuda = time_reference_cuda(inp, off, m, gout, args.dtype, timed, max(3, args.steps // 2), ms_fwd, ms_bwd)
+
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
@@ -472,7 +522,7 @@ def main():
                                "(BASELINE configs[1])", "dist": args.dist, "parallelism": f"roi-shard x{world}, no collective",
                    "l2": "no flush needed: 763 MB of inputs per step >> 126 MB L2",
                    "algorithmic_bytes_per_step": fwd_b + bwd_b},
-        "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "posenet": posenet,
+        "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_kernels": ref_cuda, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "posenet": posenet,
         "wall_s_timed_region": round(t_wall, 3),
     }
     print(json.dumps(line), flush=True)

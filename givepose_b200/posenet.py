@@ -844,8 +844,8 @@ def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo, eps=1e-4):
     if is_allo:
         ray = trans / (trans.norm(dim=1, keepdim=True) + eps)
         angle = ray[:, 2:3].acos()
-        cam_ray = torch.tensor([0.0, 0.0, 1.0], dtype=trans.dtype, device=trans.device).expand_as(ray)
-        axis = torch.cross(cam_ray, ray, dim=-1)
+        # cross((0, 0, 1), ray) written out: no host-built constant, so the step can be captured in a CUDA graph
+        axis = torch.stack((-ray[:, 1], ray[:, 0], torch.zeros_like(ray[:, 2])), dim=1)
         axis = axis / (axis.norm(dim=1, keepdim=True) + eps)
         q = torch.cat([torch.cos(angle / 2.0), axis * torch.sin(angle / 2.0)], dim=1)
         q = q / q.norm(p=2, dim=1, keepdim=True)

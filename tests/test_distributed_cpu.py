@@ -76,3 +76,23 @@ def test_gradient_allreduce_bucket_gloo_world2():
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
         assert dict(out) == {0: (True, (6 * 5 + 5 + 5 * 2 + 2 + 6) * 4), 1: (True, (6 * 5 + 5 + 5 * 2 + 2 + 6) * 4)}
+
+
+def test_bucket_clip_equals_clip_grad_norm():
+    """GradBucket.clip_ == torch.nn.utils.clip_grad_norm_ (engine/train.py:126) on the same gradients, both when the
+    norm exceeds the bound and when it does not; parameters without a gradient count as zeros."""
+    for scale in (10.0, 1e-3):
+        torch.manual_seed(1)
+        net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+        unused = torch.nn.BatchNorm1d(3)
+        ref = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.Tanh(), torch.nn.Linear(5, 2))
+        ref.load_state_dict(net.state_dict())
+        bucket = GradBucket(list(net.parameters()) + list(unused.parameters()))
+        x = torch.randn(7, 6) * scale
+        net(x).square().sum().backward()
+        ref(x).square().sum().backward()
+        n_ref = torch.nn.utils.clip_grad_norm_(ref.parameters(), 5.0)
+        n = bucket.clip_(5.0)
+        assert torch.allclose(n, n_ref, rtol=1e-6)
+        for a, b in zip(net.parameters(), ref.parameters()):
+            assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-8)

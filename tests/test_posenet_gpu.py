@@ -366,3 +366,61 @@ def test_train_step_single_rank_updates_weights(OP):
     l0 = float(train_step(net, data, tgt, opt, bucket, "cuda"))
     l1 = float(train_step(net, data, tgt, opt, bucket, "cuda"))
     assert torch.isfinite(torch.tensor([l0, l1])).all() and not torch.equal(before, net.pnp_net.fc_r.weight.detach())
+
+
+def test_graphed_train_step_matches_eager_steps(OP):
+    """The CUDA-graph replay of the training step must do what the eager step does: two nets with identical weights take
+    the same 5 steps (3 warm-up + capture... the capture itself does not execute) eagerly / as warm-up + replays; fp32 mode
+    so the only differences are atomic-order effects in the DCNv3 backward and cuDNN algorithm choices."""
+    from givepose_b200.loss import PoseLoss, make_loss_inputs
+    from givepose_b200.train import GradBucket, GraphedTrainStep, train_step
+    B, n_replay = 8, 2
+    data = {k: v.cuda() for k, v in OP.make_inputs(B, seed=5).items()}
+    tgt = {k: v.cuda() for k, v in make_loss_inputs(B, seed=5).items()}
+    crit = PoseLoss().cuda()
+    results = []
+    for graphed in (False, True):
+        torch.manual_seed(0)
+        _, net = build(OP, "o1", precision="fp32")
+        for m in net.modules():   # Dropout draws differ between an eager and a captured RNG stream
+            if isinstance(m, torch.nn.Dropout):
+                m.p = 0.0
+        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
+        bucket = GradBucket(net.parameters())
+        if graphed:
+            step = GraphedTrainStep(net, opt, bucket, "cuda", data, tgt, criterion=crit, warmup=3)
+            for _ in range(n_replay):
+                loss = step(data, tgt)
+        else:
+            for _ in range(3 + n_replay):
+                loss = train_step(net, data, tgt, opt, bucket, "cuda", criterion=crit)
+        torch.cuda.synchronize()
+        results.append((float(loss), {k: v.detach().clone() for k, v in net.named_parameters()}))
+    (l_e, p_e), (l_g, p_g) = results
+    assert abs(l_e - l_g) <= 1e-3 * abs(l_e), (l_e, l_g)
+    for name in ("pnp_net.fc_r.weight", "nocs_encoder.features.0.dcnv3.offset.weight", "xyz_nocs_head.out_layer.weight",
+                 "xyz_deform_head.features.0.weight", "backbone.neck.weight"):
+        d = (p_e[name] - p_g[name]).norm() / p_e[name].norm()
+        assert d < 1e-4, (name, float(d))
+
+
+def test_graphed_train_step_refreshes_inputs_and_does_not_sync(OP):
+    from givepose_b200.loss import PoseLoss, make_loss_inputs
+    from givepose_b200.train import GradBucket, GraphedTrainStep
+    B = 4
+    mk = lambda s: ({k: v.cuda() for k, v in OP.make_inputs(B, seed=s).items()}, {k: v.cuda() for k, v in make_loss_inputs(B, seed=s).items()})
+    (d0, t0), (d1, t1) = mk(1), mk(2)
+    _, net = build(OP, "o1", precision="bf16")
+    opt = torch.optim.SGD(net.parameters(), lr=0.0)   # weights frozen: the loss depends on the inputs only
+    step = GraphedTrainStep(net, opt, GradBucket(net.parameters()), "cuda", d0, t0, criterion=PoseLoss().cuda(), warmup=2)
+    net.eval()   # nothing below may re-run Python: the graph is what executes
+    torch.cuda.synchronize()
+    torch.cuda.set_sync_debug_mode("error")
+    try:
+        la = step(d0, t0).clone()
+        lb = step(d1, t1).clone()
+        lc = step(d0, t0).clone()
+    finally:
+        torch.cuda.set_sync_debug_mode("default")
+    la, lb, lc = float(la), float(lb), float(lc)
+    assert la != lb and abs(la - lc) <= 2e-2 * abs(la), (la, lb, lc)   # dropout draws differ between replays
