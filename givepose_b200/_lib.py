@@ -45,6 +45,8 @@ EXPORTS = {
     "gp_smallk_dwconv3x3_ln_gelu": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _I, _VP]),
     "gp_groupnorm_workspace_floats": (_SZ, [_I, _I, _I, _I]),
     "gp_groupnorm_act": (_I, [_VP, _VP, _VP, _SZ, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _VP]),
+    "gp_groupnorm_backward_workspace_floats": (_SZ, [_I, _I, _I, _I, _I]),
+    "gp_groupnorm_act_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "gp_groupnorm_act_conv1x1": (_I, [_VP, _VP, _VP, _SZ, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _I, _VP]),
     "gp_linear_bf16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, ctypes.c_float, _VP]),
     "gp_mhsa_tokens": (_I, [_VP, _VP, _I, _I, _I, _I, ctypes.c_float, _I, _VP]),

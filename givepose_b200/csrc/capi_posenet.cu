@@ -135,6 +135,46 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, 
     return (int)cudaGetLastError();
 }
 
+size_t gp_groupnorm_backward_workspace_floats(int N, int H, int W, int C, int G) {
+    if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || G <= 0) return 0;
+    int ppc = 0;
+    const dim3 sgrid = slab_grid(N, H * W, 8, &ppc);
+    return (size_t)N * G * 2 + (size_t)N * sgrid.x * C * 2;   // (A, B)/cnt per (n, g) followed by the per-channel slab partials
+}
+
+int gp_groupnorm_act_backward(const void *x, const void *dy, const float *stats, const float *gamma, const float *beta, void *dx,
+                              float *dgamma, float *dbeta, float *ws, size_t ws_floats, int N, int H, int W, int C, int G, int act,
+                              int dtype, void *stream) {
+    if (!x || !dy || !stats || !gamma || !beta || !dx || !dgamma || !dbeta || !ws) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || C % G || (C / G) % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (act < 0 || act > 2) return GP_ERR_UNSUPPORTED;
+    if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;
+    if (!al16(x) || !al16(dy) || !al16(dx)) return GP_ERR_ALIGN;
+    if (ws_floats < gp_groupnorm_backward_workspace_floats(N, H, W, C, G)) return GP_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int HW = H * W;
+    int sppc = 0, appc = 0;
+    const dim3 sgrid = slab_grid(N, HW, 8, &sppc);
+    const dim3 agrid = slab_grid(N, HW, 16, &appc);
+    float *gstat = ws, *partial = ws + (size_t)N * G * 2;
+#define GP_GNB(TT, AA) do { \
+        gn_bwd_stats_kernel<TT, AA><<<sgrid, 256, 256 * 8 * sizeof(float), st>>>((const TT *)x, (const TT *)dy, stats, gamma, beta, partial, HW, C, G, sppc); \
+        gn_bwd_group_kernel<<<(N * G + 127) / 128, 128, 0, st>>>(partial, gamma, gstat, N * G, G, C, (int)sgrid.x, 1.f / ((float)HW * (C / G))); \
+        gn_bwd_param_kernel<<<(C + 7) / 8, 256, 0, st>>>(partial, dgamma, dbeta, C, N * (int)sgrid.x); \
+        gn_bwd_apply_kernel<TT, AA><<<agrid, 256, 0, st>>>((const TT *)x, (const TT *)dy, stats, gstat, gamma, beta, (TT *)dx, HW, C, G, appc); } while (0)
+#define GP_GNB_T(TT) do { if (act == ACT_RELU) GP_GNB(TT, ACT_RELU); else if (act == ACT_GELU) GP_GNB(TT, ACT_GELU); else GP_GNB(TT, ACT_NONE); } while (0)
+    switch (dtype) {
+        case GP_F32: GP_GNB_T(float); break;
+        case GP_BF16: GP_GNB_T(__nv_bfloat16); break;
+        case GP_F16: GP_GNB_T(__half); break;
+        default: return GP_ERR_DTYPE;
+    }
+#undef GP_GNB_T
+#undef GP_GNB
+    count_launch(4);
+    return (int)cudaGetLastError();
+}
+
 int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
                              const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
                              int dtype, void *stream) {

@@ -396,6 +396,158 @@ gn_apply_kernel(const T *__restrict__ x, const float *__restrict__ stats, const 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Backward of y = act(GroupNorm(x)) for the training step (replaces torch's native_group_norm_backward + gelu_backward /
+// threshold_backward + the fp32 <-> bf16 copies autocast wraps around them).  With z = xhat*gamma + beta,
+// xhat = (x - mean)*rstd, dz = dy * act'(z) (z is recomputed, nothing but x and the (mean, rstd) pairs is saved):
+//   dgamma[c] = sum_{n,p} dz*xhat      dbeta[c] = sum_{n,p} dz
+//   A[n,g] = sum_{p, c in g} dz*gamma  B[n,g] = sum_{p, c in g} dz*gamma*xhat
+//   dx = rstd * (dz*gamma - (A + xhat*B) / (HW*cg))
+//   pass 1 (gn_bwd_stats):   per (n, slab, c): sum dz, sum dz*xhat  -> partial[n][slab][c][2]  (fixed order, no atomics)
+//   finalize (gn_bwd_group): per (n, g): A/cnt, B/cnt -> gstat[n][g][2];  (gn_bwd_param): one warp per channel -> dgamma, dbeta
+//   pass 2 (gn_bwd_apply):   dx
+// ---------------------------------------------------------------------------------------------------
+template <typename T, int ACT> __device__ __forceinline__ float gn_act_grad(float z) {
+    if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (ACT == ACT_GELU) {   // d/dz [z Phi(z)] = Phi(z) + z phi(z); erf as in gelu_erf (A&S 7.1.26), exp(-z^2/2) shared
+        const float a = fabsf(z) * 0.70710678118654752440f;
+        const float t = __frcp_rn(fmaf(0.3275911f, a, 1.f));
+        float poly = fmaf(1.061405429f, t, -1.453152027f);
+        poly = fmaf(poly, t, 1.421413741f);
+        poly = fmaf(poly, t, -0.284496736f);
+        poly = fmaf(poly, t, 0.254829592f);
+        const float E = __expf(-0.5f * z * z);
+        const float erf_abs = 1.f - poly * t * E;
+        const float Phi = 0.5f + copysignf(0.5f * erf_abs, z);
+        return fmaf(z * 0.39894228040143267794f, E, Phi);
+    }
+    return 1.f;
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256)
+gn_bwd_stats_kernel(const T *__restrict__ x, const T *__restrict__ dy, const float *__restrict__ stats, const float *__restrict__ gamma,
+                    const float *__restrict__ beta, float *__restrict__ partial /*[N][slabs][C][2]*/, int HW, int C, int G,
+                    int pix_per_cta) {
+    extern __shared__ float s_thr[];   // [blockDim][8]
+    const int n = blockIdx.y;
+    const int q = C / 4, cq = threadIdx.x % q, prow = threadIdx.x / q, pstep = blockDim.x / q;
+    const int cg = C / G;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    float s1[4] = {0.f, 0.f, 0.f, 0.f}, s2[4] = {0.f, 0.f, 0.f, 0.f};
+    if (prow < pstep) {
+        float sc[4], sh[4], mean[4], rstd[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c = 4 * cq + k, g = c / cg;
+            mean[k] = stats[((long long)n * G + g) * 2];
+            rstd[k] = stats[((long long)n * G + g) * 2 + 1];
+            sc[k] = rstd[k] * __ldg(gamma + c);
+            sh[k] = __ldg(beta + c) - mean[k] * sc[k];
+        }
+        for (int p = p0 + prow; p < p1; p += pstep) {
+            float v[4], d[4];
+            const long long o = ((long long)n * HW + p) * C + 4 * cq;
+            Vec4IO<T>::ld(x + o, v);
+            Vec4IO<T>::ld(dy + o, d);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float dz = d[k] * gn_act_grad<T, ACT>(fmaf(v[k], sc[k], sh[k]));
+                s1[k] += dz;
+                s2[k] = fmaf(dz, (v[k] - mean[k]) * rstd[k], s2[k]);
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        s_thr[8 * threadIdx.x + 2 * k] = s1[k];
+        s_thr[8 * threadIdx.x + 2 * k + 1] = s2[k];
+    }
+    __syncthreads();
+    // entry i = (channel c, which): the pstep pixel rows of quad c/4, in row order
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        const int c = i >> 1;
+        float a = 0.f;
+        for (int r = 0; r < pstep; ++r) a += s_thr[8 * (r * q + (c >> 2)) + 2 * (c & 3) + (i & 1)];
+        partial[(((long long)n * gridDim.x + blockIdx.x) * C + c) * 2 + (i & 1)] = a;
+    }
+}
+
+__global__ void __launch_bounds__(128)
+gn_bwd_group_kernel(const float *__restrict__ partial, const float *__restrict__ gamma, float *__restrict__ gstat /*[N][G][2]*/,
+                    int NG, int G, int C, int slabs, float inv_cnt) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= NG) return;
+    const int n = i / G, g = i - n * G, cg = C / G;
+    float A = 0.f, B = 0.f;
+    for (int k = 0; k < slabs; ++k)
+        for (int j = 0; j < cg; ++j) {
+            const int c = g * cg + j;
+            const float *pp = partial + (((long long)n * slabs + k) * C + c) * 2;
+            const float gm = __ldg(gamma + c);
+            A = fmaf(gm, pp[0], A);
+            B = fmaf(gm, pp[1], B);
+        }
+    gstat[2 * i] = A * inv_cnt;
+    gstat[2 * i + 1] = B * inv_cnt;
+}
+
+// one warp per channel: lanes stride over the (n, slab) partials, then a fixed-order butterfly
+__global__ void __launch_bounds__(256)
+gn_bwd_param_kernel(const float *__restrict__ partial, float *__restrict__ dgamma, float *__restrict__ dbeta, int C, int n_slabs_total) {
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (c >= C) return;
+    float b = 0.f, g = 0.f;
+    for (int k = lane; k < n_slabs_total; k += 32) {
+        const float2 v = *reinterpret_cast<const float2 *>(partial + ((long long)k * C + c) * 2);
+        b += v.x;
+        g += v.y;
+    }
+    b = warp_sum(b);
+    g = warp_sum(g);
+    if (lane == 0) {
+        dbeta[c] = b;
+        dgamma[c] = g;
+    }
+}
+
+template <typename T, int ACT>
+__global__ void __launch_bounds__(256)
+gn_bwd_apply_kernel(const T *__restrict__ x, const T *__restrict__ dy, const float *__restrict__ stats, const float *__restrict__ gstat,
+                    const float *__restrict__ gamma, const float *__restrict__ beta, T *__restrict__ dx, int HW, int C, int G,
+                    int pix_per_cta) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int n = blockIdx.y;
+    const int q = C / V, cq = threadIdx.x % q, prow = threadIdx.x / q, pstep = blockDim.x / q;
+    if (prow >= pstep) return;
+    const int cg = C / G;
+    // dx = dz * (rstd*gamma) - rstd*(A' + xhat*B'),  xhat = x*rstd - mean*rstd  ->  dx = dz*sc - (x*c1 + c0)
+    float sc[V], sh[V], c0[V], c1[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = V * cq + k, g = c / cg;
+        const float mean = stats[((long long)n * G + g) * 2], rstd = stats[((long long)n * G + g) * 2 + 1];
+        const float A = gstat[((long long)n * G + g) * 2], B = gstat[((long long)n * G + g) * 2 + 1];
+        sc[k] = rstd * __ldg(gamma + c);
+        sh[k] = __ldg(beta + c) - mean * sc[k];
+        c1[k] = rstd * rstd * B;
+        c0[k] = rstd * (A - mean * rstd * B);
+    }
+    const long long base = (long long)n * HW * C + V * cq;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(HW, p0 + pix_per_cta);
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        float v[V], d[V];
+        Vec<T, V>::load(x + base + (long long)p * C, v);
+        Vec<T, V>::load_stream(dy + base + (long long)p * C, d);
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            const float dz = d[k] * gn_act_grad<T, ACT>(fmaf(v[k], sc[k], sh[k]));
+            d[k] = fmaf(dz, sc[k], -fmaf(v[k], c1[k], c0[k]));
+        }
+        Vec<T, V>::store_stream(dx + base + (long long)p * C, d);
+    }
+}
+
 // GroupNorm -> act -> 1x1 convolution to OC (<= 4) channels + bias, for the decoder's out_layer (xyz_head.py:349-366:
 // the last ConvModule's GN + GELU followed by Conv1x1 256 -> 3): the normalised 256-channel activation is never written.
 // One warp per pixel, lane = C/32 consecutive channels; the OC dot products are reduced with warp shuffles.

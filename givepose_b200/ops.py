@@ -94,7 +94,7 @@ def _nhwc(name, x):
     return dt
 
 
-def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=False):
+def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=False, return_stats=False):
     """``act(GroupNorm(x))`` on channel-last ``x`` (N,H,W,C); ``upsample2x`` appends the align_corners=True bilinear x2
     upsampling of ``TopDownXyzHead`` (a second pass: see posenet_kernels.cuh).  ``gamma`` / ``beta`` are fp32."""
     dt = _nhwc("input", x)
@@ -106,7 +106,50 @@ def groupnorm_act(x, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=Fa
     with torch.cuda.device(x.device):
         check(lib.gp_groupnorm_act(_vp(x), _vp(y), _vp(stats), stats.numel(), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
                                    ACT[act], dt, _stream(x)), "groupnorm_act")
-    return upsample_bilinear2x(y) if upsample2x else y
+    y = upsample_bilinear2x(y) if upsample2x else y
+    return (y, stats[:N * int(groups) * 2]) if return_stats else y
+
+
+def groupnorm_act_backward(x, dy, stats, gamma, beta, groups=32, act="none"):
+    """Gradients of ``groupnorm_act`` (without the upsampling): ``(dx, dgamma, dbeta)``; ``stats`` is what the forward returned
+    with ``return_stats=True``.  ``dx`` has ``x``'s dtype, ``dgamma`` / ``dbeta`` are fp32."""
+    dt = _nhwc("input", x)
+    _need_cuda("grad_output", dy, x.dtype)
+    for n, t in (("stats", stats), ("gn weight", gamma), ("gn bias", beta)):
+        _need_cuda(n, t, torch.float32)
+    N, H, W, C = x.shape
+    if dy.shape != x.shape or stats.numel() < N * int(groups) * 2:
+        raise RuntimeError("groupnorm_act_backward: inconsistent shapes")
+    dx = torch.empty_like(x)
+    dgamma = torch.empty(C, dtype=torch.float32, device=x.device)
+    dbeta = torch.empty(C, dtype=torch.float32, device=x.device)
+    ws = torch.empty(lib.gp_groupnorm_backward_workspace_floats(N, H, W, C, int(groups)), dtype=torch.float32, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_groupnorm_act_backward(_vp(x), _vp(dy), _vp(stats), _vp(gamma), _vp(beta), _vp(dx), _vp(dgamma), _vp(dbeta), _vp(ws),
+                                            ws.numel(), N, H, W, C, int(groups), ACT[act], dt, _stream(x)), "groupnorm_act_backward")
+    return dx, dgamma, dbeta
+
+
+class GroupNormAct(torch.autograd.Function):
+    """``act(GroupNorm(x))`` on channel-last activations as ONE autograd node for the training step: forward = the inference
+    kernels, backward = ``groupnorm_act_backward``.  Only ``x`` (storage dtype) and the (mean, rstd) pairs are saved; torch's
+    eager path keeps the fp32 GroupNorm output and the activation input alive and, under autocast, wraps both in dtype copies."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, groups, eps, act):
+        xc = x.contiguous()
+        g32, b32 = gamma.detach().float().contiguous(), beta.detach().float().contiguous()
+        y, stats = groupnorm_act(xc, g32, b32, groups, eps, act, return_stats=True)
+        ctx.save_for_backward(xc, stats, g32, b32)
+        ctx.groups, ctx.act, ctx.pdtype = groups, act, gamma.dtype
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        x, stats, g32, b32 = ctx.saved_tensors
+        dx, dg, db = groupnorm_act_backward(x, dy.to(x.dtype).contiguous(), stats, g32, b32, ctx.groups, ctx.act)
+        return dx, dg.to(ctx.pdtype), db.to(ctx.pdtype), None, None, None
 
 
 def groupnorm_act_conv1x1(x, gamma, beta, weight, bias, groups=32, eps=1e-5, act="gelu"):

@@ -154,6 +154,16 @@ size_t gp_groupnorm_workspace_floats(int N, int H, int W, int G);
 int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N,
                      int H, int W, int C, int G, float eps, int act, int dtype, void *stream);
 
+/* Backward of gp_groupnorm_act for the training step (replaces torch's native_group_norm_backward + gelu/threshold
+ * backward that follow `get_norm("GN")` / `get_nn_act_func` under autograd, layer_utils.py:32-94).  stats = the first N*G*2
+ * floats gp_groupnorm_act left in its scratch ((mean, rstd) per (n, group)); x is the forward INPUT, dy the gradient of the
+ * activation output (same dtype / layout as x); dx gets the input gradient, dgamma / dbeta [C] fp32 are OVERWRITTEN.
+ * ws: scratch of gp_groupnorm_backward_workspace_floats floats.  No atomics: bit-reproducible. */
+size_t gp_groupnorm_backward_workspace_floats(int N, int H, int W, int C, int G);
+int gp_groupnorm_act_backward(const void *x, const void *dy, const float *stats, const float *gamma, const float *beta, void *dx,
+                              float *dgamma, float *dbeta, float *ws, size_t ws_floats, int N, int H, int W, int C, int G, int act,
+                              int dtype, void *stream);
+
 /* y = Conv1x1_{C->OC}(act(GroupNorm_G(x))) + bias: the decoder's last ConvModule norm/activation fused with its
  * out_layer (xyz_head.py:349-366, Conv1x1 256 -> 3); the normalised C-channel activation is never written.
  * x (N,H,W,C) channel-last, y (N,H,W,OC) of `dtype`; w [OC][C] and bias [OC] fp32.  Supported: C == 256, OC == 3.

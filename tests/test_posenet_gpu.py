@@ -368,40 +368,38 @@ def test_train_step_single_rank_updates_weights(OP):
     assert torch.isfinite(torch.tensor([l0, l1])).all() and not torch.equal(before, net.pnp_net.fc_r.weight.detach())
 
 
-def test_graphed_train_step_matches_eager_steps(OP):
-    """The CUDA-graph replay of the training step must do what the eager step does: two nets with identical weights take
-    the same 5 steps (3 warm-up + capture... the capture itself does not execute) eagerly / as warm-up + replays; fp32 mode
-    so the only differences are atomic-order effects in the DCNv3 backward and cuDNN algorithm choices."""
+def test_graphed_train_step_matches_eager_step(OP):
+    """The CUDA-graph replay of the training step must do what the eager step does.  Weights frozen (lr 0), fp32 mode: the
+    loss and the clipped gradient bucket of a replay equal those of an eager step (differences: atomic order in the DCNv3
+    backward, cuDNN algorithm choice).  Then with lr > 0 every replay moves the weights (the optimizer step is in the graph)."""
     from givepose_b200.loss import PoseLoss, make_loss_inputs
     from givepose_b200.train import GradBucket, GraphedTrainStep, train_step
-    B, n_replay = 8, 2
+    B = 8
     data = {k: v.cuda() for k, v in OP.make_inputs(B, seed=5).items()}
     tgt = {k: v.cuda() for k, v in make_loss_inputs(B, seed=5).items()}
     crit = PoseLoss().cuda()
-    results = []
-    for graphed in (False, True):
-        torch.manual_seed(0)
-        _, net = build(OP, "o1", precision="fp32")
-        for m in net.modules():   # Dropout draws differ between an eager and a captured RNG stream
-            if isinstance(m, torch.nn.Dropout):
-                m.p = 0.0
-        opt = torch.optim.SGD(net.parameters(), lr=1e-3, momentum=0.9)
-        bucket = GradBucket(net.parameters())
-        if graphed:
-            step = GraphedTrainStep(net, opt, bucket, "cuda", data, tgt, criterion=crit, warmup=3)
-            for _ in range(n_replay):
-                loss = step(data, tgt)
-        else:
-            for _ in range(3 + n_replay):
-                loss = train_step(net, data, tgt, opt, bucket, "cuda", criterion=crit)
-        torch.cuda.synchronize()
-        results.append((float(loss), {k: v.detach().clone() for k, v in net.named_parameters()}))
-    (l_e, p_e), (l_g, p_g) = results
-    assert abs(l_e - l_g) <= 1e-3 * abs(l_e), (l_e, l_g)
-    for name in ("pnp_net.fc_r.weight", "nocs_encoder.features.0.dcnv3.offset.weight", "xyz_nocs_head.out_layer.weight",
-                 "xyz_deform_head.features.0.weight", "backbone.neck.weight"):
-        d = (p_e[name] - p_g[name]).norm() / p_e[name].norm()
-        assert d < 1e-4, (name, float(d))
+    _, net = build(OP, "o1", precision="fp32")
+    for m in net.modules():   # Dropout draws differ between an eager and a captured RNG stream
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
+    opt = torch.optim.SGD(net.parameters(), lr=0.0, momentum=0.9)
+    bucket = GradBucket(net.parameters())
+    l_e = float(train_step(net, data, tgt, opt, bucket, "cuda", criterion=crit))
+    g_e = bucket.flat.clone()
+    step = GraphedTrainStep(net, opt, bucket, "cuda", data, tgt, criterion=crit, warmup=1)
+    bucket.flat.fill_(123.0)   # the replay has to zero and refill it
+    l_g = float(step(data, tgt))
+    g_g = bucket.flat.clone()
+    assert abs(l_e - l_g) <= 1e-5 * abs(l_e), (l_e, l_g)
+    assert float(g_e.norm()) > 0 and float((g_e - g_g).norm() / g_e.norm()) < 5e-3   # measured 1.2e-3: atomic order + cuDNN algorithm choice
+    for group in opt.param_groups:
+        group["lr"] = 1e-3   # read at capture time: a new capture is needed for a new learning rate
+    step = GraphedTrainStep(net, opt, bucket, "cuda", data, tgt, criterion=crit, warmup=1)
+    w0 = net.pnp_net.fc_r.weight.detach().clone()
+    step()
+    w1 = net.pnp_net.fc_r.weight.detach().clone()
+    step()
+    assert not torch.equal(w0, w1) and not torch.equal(w1, net.pnp_net.fc_r.weight.detach())
 
 
 def test_graphed_train_step_refreshes_inputs_and_does_not_sync(OP):
@@ -411,6 +409,9 @@ def test_graphed_train_step_refreshes_inputs_and_does_not_sync(OP):
     mk = lambda s: ({k: v.cuda() for k, v in OP.make_inputs(B, seed=s).items()}, {k: v.cuda() for k, v in make_loss_inputs(B, seed=s).items()})
     (d0, t0), (d1, t1) = mk(1), mk(2)
     _, net = build(OP, "o1", precision="bf16")
+    for m in net.modules():   # Dropout draws differ between replays
+        if isinstance(m, torch.nn.Dropout):
+            m.p = 0.0
     opt = torch.optim.SGD(net.parameters(), lr=0.0)   # weights frozen: the loss depends on the inputs only
     step = GraphedTrainStep(net, opt, GradBucket(net.parameters()), "cuda", d0, t0, criterion=PoseLoss().cuda(), warmup=2)
     net.eval()   # nothing below may re-run Python: the graph is what executes
@@ -423,4 +424,34 @@ def test_graphed_train_step_refreshes_inputs_and_does_not_sync(OP):
     finally:
         torch.cuda.set_sync_debug_mode("default")
     la, lb, lc = float(la), float(lb), float(lc)
-    assert la != lb and abs(la - lc) <= 2e-2 * abs(la), (la, lb, lc)   # dropout draws differ between replays
+    assert la != lb and abs(la - lc) <= 2e-3 * abs(la), (la, lb, lc)   # atomics order in the DCNv3 backward does not touch the loss
+
+
+@pytest.mark.parametrize("shape,groups", [((4, 16, 16, 256), 32), ((3, 8, 8, 128), 32), ((2, 64, 64, 256), 32), ((5, 7, 9, 64), 4)])
+@pytest.mark.parametrize("act", ["none", "relu", "gelu"])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)], ids=["f32", "bf16"])
+def test_groupnorm_act_autograd_matches_torch(shape, groups, act, dtype, tol):
+    """ops.GroupNormAct (our forward + backward kernels, one autograd node) vs torch's fp32 group_norm + activation autograd
+    on the same (rounded) inputs: y, dx, dgamma, dbeta.  Tolerance relative to each tensor's max; bf16 = storage rounding."""
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(7)
+    N, H, W, C = shape
+    x = (torch.randn(shape, generator=g) * 1.5 + 0.3).to(dtype).cuda()
+    gamma = (torch.rand(C, generator=g) + 0.5).cuda().requires_grad_(True)
+    beta = (torch.randn(C, generator=g) * 0.2).cuda().requires_grad_(True)
+    dy = torch.randn(shape, generator=g).to(dtype).cuda()
+    xa = x.clone().requires_grad_(True)
+    y = ops.GroupNormAct.apply(xa, gamma, beta, groups, 1e-5, act)
+    assert y.dtype == dtype and y.shape == x.shape
+    y.backward(dy)
+    got = (y.detach(), xa.grad, gamma.grad.clone(), beta.grad.clone())
+    gamma.grad = beta.grad = None
+    xr = x.float().clone().requires_grad_(True)
+    yr = torch.nn.functional.group_norm(xr.permute(0, 3, 1, 2), groups, gamma, beta, 1e-5)
+    yr = torch.relu(yr) if act == "relu" else torch.nn.functional.gelu(yr) if act == "gelu" else yr
+    yr = yr.permute(0, 2, 3, 1)
+    yr.backward(dy.float())
+    want = (yr.detach(), xr.grad, gamma.grad, beta.grad)
+    for a, b, name in zip(got, want, ("y", "dx", "dgamma", "dbeta")):
+        err = ((a.float() - b).abs().max() / b.abs().max()).item()
+        assert err < tol, (name, err)

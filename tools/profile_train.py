@@ -36,4 +36,6 @@ ka = prof.key_averages()
 dev_ms = sum(e.self_device_time_total for e in ka) / 1e3
 n_k = sum(e.count for e in ka if e.self_device_time_total > 0)
 print(f"device-busy {dev_ms:.2f} ms in {n_k} kernels/memcpys")
-print(ka.table(sort_by="self_cuda_time_total", row_limit=25, max_name_column_width=80))
+rows = sorted((e for e in ka if e.self_device_time_total > 0), key=lambda e: -e.self_device_time_total)
+for e in rows[:45]:
+    print(f"{e.self_device_time_total / 1e3:8.3f} ms {e.count:5d} x  {e.key[:150]}")
