@@ -221,6 +221,24 @@ int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, i
     return (int)cudaGetLastError();
 }
 
+int gp_upsample_bilinear2x_backward(const void *dy, void *dx, int N, int H, int W, int C, int dtype, void *stream) {
+    if (!dy || !dx) return GP_ERR_NULL;
+    if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || C % 4 || C / 4 > 256) return GP_ERR_SHAPE;
+    if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;
+    if (!al16(dy) || !al16(dx)) return GP_ERR_ALIGN;
+    cudaStream_t st = (cudaStream_t)stream;
+    int ppc = 0;
+    const dim3 grid = slab_grid(N, H * W, 16, &ppc);
+    switch (dtype) {
+        case GP_F32: upsample2x_bwd_kernel<float><<<grid, 256, 0, st>>>((const float *)dy, (float *)dx, H, W, C, ppc); break;
+        case GP_BF16: upsample2x_bwd_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)dy, (__nv_bfloat16 *)dx, H, W, C, ppc); break;
+        case GP_F16: upsample2x_bwd_kernel<__half><<<grid, 256, 0, st>>>((const __half *)dy, (__half *)dx, H, W, C, ppc); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int gp_stem_s2d_pack(const float *img, void *out, int N, int H, int W, int dtype, void *stream) {
     if (!img || !out) return GP_ERR_NULL;
     if (N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2) return GP_ERR_SHAPE;

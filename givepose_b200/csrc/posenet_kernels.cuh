@@ -626,6 +626,57 @@ upsample2x_kernel(const T *__restrict__ x, T *__restrict__ y, int H, int W, int 
     }
 }
 
+// Backward of upsample2x_kernel as a GATHER (deterministic, no atomics): input pixel (iy, ix) collects
+// wy(oh, iy) * wx(ow, ix) * dy[oh, ow] over the <= 6 x 6 output pixels whose 2x2 source footprint contains it; the weights
+// are recomputed with exactly the forward's expressions, so forward and backward are transposes of each other bit for bit.
+template <typename T>
+__global__ void __launch_bounds__(256)
+upsample2x_bwd_kernel(const T *__restrict__ dy, T *__restrict__ dx, int H, int W, int C, int pix_per_cta) {
+    constexpr int V = 16 / (int)sizeof(T), R = 6;
+    const int n = blockIdx.y;
+    const int q = C / V, cq = threadIdx.x % q, prow = threadIdx.x / q, pstep = blockDim.x / q;
+    if (prow >= pstep) return;
+    const int Ho = 2 * H, Wo = 2 * W;
+    const float ry = (float)(H - 1) / (float)(Ho - 1), rx = (float)(W - 1) / (float)(Wo - 1);
+    const T *g = dy + (long long)n * Ho * Wo * C + V * cq;
+    T *out = dx + (long long)n * H * W * C + V * cq;
+    const int p0 = blockIdx.x * pix_per_cta, p1 = min(H * W, p0 + pix_per_cta);
+    auto weight = [](int o, int i, float r, int n_in) {   // contribution of output index o to input index i (forward's y0/y1/ly)
+        const float f = (float)o * r;
+        const int i0 = min((int)f, n_in - 1), i1 = min(i0 + 1, n_in - 1);
+        const float l = f - (float)i0;
+        return (i0 == i ? 1.f - l : 0.f) + (i1 == i ? l : 0.f);
+    };
+    for (int p = p0 + prow; p < p1; p += pstep) {
+        const int iy = p / W, ix = p - iy * W;
+        // outputs with source coordinate in (i-1, i+1): o in ((i-1)/r, (i+1)/r); r ~ 1/2 -> at most 5, R = 6 with slack
+        const int oy0 = max(0, (int)floorf((float)(iy - 1) / fmaxf(ry, 1e-6f))), ox0 = max(0, (int)floorf((float)(ix - 1) / fmaxf(rx, 1e-6f)));
+        float wy[R], wx[R];
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            wy[t] = oy0 + t < Ho ? weight(oy0 + t, iy, ry, H) : 0.f;
+            wx[t] = ox0 + t < Wo ? weight(ox0 + t, ix, rx, W) : 0.f;
+        }
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+#pragma unroll
+        for (int a = 0; a < R; ++a) {
+            if (wy[a] == 0.f) continue;
+#pragma unroll
+            for (int b = 0; b < R; ++b) {
+                if (wx[b] == 0.f) continue;
+                float v[V];
+                Vec<T, V>::load(g + ((long long)(oy0 + a) * Wo + ox0 + b) * C, v);
+                const float w = wy[a] * wx[b];
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] = fmaf(w, v[k], acc[k]);
+            }
+        }
+        Vec<T, V>::store_stream(out + (long long)p * C, acc);
+    }
+}
+
 // Input packing for the stand-in backbone's 7x7 / stride-2 / pad-3 stem (network/resnet.py:104): cuDNN has no tensor-core
 // kernel worth the name for 3 input channels (10.6 ms per 1024 RoIs on B200, 16 % of the whole forward).  The same
 // convolution is a 4x4 / stride-1 convolution over the 2x2 space-to-depth image (kernel padded 7 -> 8 with a zero tap in

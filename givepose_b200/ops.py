@@ -231,6 +231,31 @@ def upsample_bilinear2x(x):
     return y
 
 
+def upsample_bilinear2x_backward(dy):
+    """Gradient of ``upsample_bilinear2x`` w.r.t. its input: ``dy`` (N,2H,2W,C) -> (N,H,W,C); a gather, no atomics."""
+    dt = _nhwc("grad_output", dy)
+    N, Ho, Wo, C = dy.shape
+    if Ho % 2 or Wo % 2:
+        raise RuntimeError("upsample_bilinear2x_backward: odd output size")
+    dx = torch.empty((N, Ho // 2, Wo // 2, C), dtype=dy.dtype, device=dy.device)
+    with torch.cuda.device(dy.device):
+        check(lib.gp_upsample_bilinear2x_backward(_vp(dy), _vp(dx), N, Ho // 2, Wo // 2, C, dt, _stream(dy)), "upsample_bilinear2x_backward")
+    return dx
+
+
+class UpsampleBilinear2x(torch.autograd.Function):
+    """``nn.UpsamplingBilinear2d(2)`` on channel-last activations as one autograd node (training step)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return upsample_bilinear2x(x.contiguous())
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        return upsample_bilinear2x_backward(dy.contiguous())
+
+
 def maxpool3x3s2(x, relu=False):
     """``MaxPool2d(3, 2, 1)`` on channel-last ``x`` (N,H,W,C); ``relu=True`` computes ``maxpool(relu(x))`` in the same pass."""
     dt = _nhwc("input", x)

@@ -256,8 +256,7 @@ def _gn_act_nhwc(x, gn: nn.GroupNorm, act: str, upsample2x=False):
     # training step: one autograd node with our forward + backward kernels (storage dtype in and out: no fp32 round trip)
     y = ops.GroupNormAct.apply(x, gn.weight, gn.bias, gn.num_groups, gn.eps, act)
     if upsample2x:
-        # torch's channels_last bilinear kernel (forward + backward) on the NHWC buffer viewed as channels_last NCHW
-        y = F.interpolate(y.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+        y = ops.UpsampleBilinear2x.apply(y)
     return y
 
 

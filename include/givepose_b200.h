@@ -196,6 +196,8 @@ int gp_stem_s2d_pack(const float *img, void *out, int N, int H, int W, int dtype
 /* nn.UpsamplingBilinear2d(scale_factor=2) (align_corners=True) of TopDownXyzHead (xyz_head.py:262-265) on channel-last
  * activations: (N,H,W,C) -> (N,2H,2W,C). */
 int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream);
+/* Its backward as a deterministic gather: dy (N,2H,2W,C) -> dx (N,H,W,C), the exact transpose of the forward weights. */
+int gp_upsample_bilinear2x_backward(const void *dy, void *dx, int N, int H, int W, int C, int dtype, void *stream);
 
 /* MaxPool2d(3, stride 2, pad 1) on channel-last activations (stem of the stand-in ResNet backbone, resnet.py:106):
  * (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C).  relu != 0 computes maxpool(relu(x)) (= relu(maxpool(x))) in the same pass. */

@@ -455,3 +455,22 @@ def test_groupnorm_act_autograd_matches_torch(shape, groups, act, dtype, tol):
     for a, b, name in zip(got, want, ("y", "dx", "dgamma", "dbeta")):
         err = ((a.float() - b).abs().max() / b.abs().max()).item()
         assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("shape", [(3, 8, 8, 256), (2, 16, 16, 256), (2, 5, 9, 64), (1, 1, 1, 8), (1, 2, 3, 8)])
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-6), (torch.bfloat16, 1e-2)], ids=["f32", "bf16"])
+def test_upsample2x_autograd_matches_torch(shape, dtype, tol):
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(11)
+    N, H, W, C = shape
+    x = torch.randn(shape, generator=g).to(dtype).cuda()
+    dy = torch.randn(N, 2 * H, 2 * W, C, generator=g).to(dtype).cuda()
+    xa = x.clone().requires_grad_(True)
+    y = ops.UpsampleBilinear2x.apply(xa)
+    y.backward(dy)
+    xr = x.float().clone().requires_grad_(True)
+    yr = torch.nn.functional.interpolate(xr.permute(0, 3, 1, 2), scale_factor=2, mode="bilinear", align_corners=True).permute(0, 2, 3, 1)
+    yr.backward(dy.float())
+    for a, b, name in ((y.detach(), yr.detach(), "y"), (xa.grad, xr.grad, "dx")):
+        err = ((a.float() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+        assert err < tol, (name, err)
