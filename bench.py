@@ -18,6 +18,8 @@ Multi-GPU: RoIs shard across ranks (one process per GPU, torchrun); no data-path
 `--impl reference` times the reference's CPU implementation (oracle port) on rank 0 with all host threads.
 """
 import argparse
+
+import numpy as np
 import json
 import os
 import statistics
@@ -233,6 +235,64 @@ def run_posenet(args, rank, world, dev, dist):
                 pose = (res["rot"], res["trans"].cpu(), res["size"].cpu())   # rot is already on the host (reference behaviour)
             barrier()
             te = torch.tensor([(time.perf_counter() - t0) / steps], device=dev, dtype=torch.float64)
+            # image in -> pose out: uint8 frames + instance-id maps on pinned host memory -> H2D -> RoI crops
+            # on the device (givepose_b200.roi, bit-exact with the reference's OpenCV host code) -> forward -> D2H of the poses
+            img_in = None
+            if prec == "bf16":
+                from givepose_b200 import roi as groi
+                g = torch.Generator().manual_seed(77 + rank)
+                per_frame = 8
+                Mf = max(1, B // per_frame)
+                frames_h = torch.randint(0, 256, (Mf, 480, 640, 3), dtype=torch.uint8, generator=g).pin_memory()
+                inst_h = torch.randint(0, 9, (Mf, 480, 640), dtype=torch.uint8, generator=g).pin_memory()
+                y1, x1 = torch.randint(0, 300, (B,), generator=g), torch.randint(0, 400, (B,), generator=g)
+                bboxes = torch.stack([y1, x1, y1 + torch.randint(40, 180, (B,), generator=g), x1 + torch.randint(40, 240, (B,), generator=g)], 1).numpy()
+                iidx = (torch.arange(B) // per_frame).clamp(max=Mf - 1).int()
+                iid = (torch.arange(B) % per_frame + 1).int()
+                small = {k: host[k] for k in ("cam_K", "mean_size")}
+
+                def image_in_step():
+                    fr, ins = frames_h.to(dev, non_blocking=True), inst_h.to(dev, non_blocking=True)
+                    d = groi.posenet_inputs_from_detections(fr, bboxes, ins, small["cam_K"], small["mean_size"], iidx, iidx, iid)
+                    r = net(d, dev)
+                    return r["rot"], r["trans"].cpu(), r["size"].cpu()
+                image_in_step()
+                barrier()
+                t0 = time.perf_counter()
+                for _ in range(steps):
+                    image_in_step()
+                barrier()
+                ti = torch.tensor([(time.perf_counter() - t0) / steps], device=dev, dtype=torch.float64)
+                # the crop kernel alone (CUDA events): HBM-bound, algorithmic bytes = the fp32 crops it writes + the source pixels it reads
+                fr, ins = frames_h.to(dev), inst_h.to(dev)
+                geo = groi.detection_geometry(bboxes, 480, 640)
+                th = time.perf_counter()
+                aff = np.concatenate([groi.roi_affine_inverse(geo["bbox_center"], geo["img_scale"], 256),
+                                      groi.roi_affine_inverse(geo["bbox_center"], geo["img_scale"], 64)])
+                host_affine_ms = (time.perf_counter() - th) * 1e3
+                aff = torch.from_numpy(aff).to(dev)
+                iidx_d, iid_d = iidx.to(dev), iid.to(dev)
+                crop = lambda: groi.roi_crops(fr, geo["bbox_center"], geo["img_scale"], iidx_d, ins, iidx_d, iid_d, affines=aff)
+                crop()
+                torch.cuda.synchronize()
+                c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                c0.record()
+                for _ in range(5):
+                    crop()
+                c1.record()
+                torch.cuda.synchronize()
+                crop_ms = c0.elapsed_time(c1) / 5   # the kernel (+ output allocation, table upload): matrices precomputed
+                crop_bytes = B * (4 * 256 * 256 * 4 + 2 * 64 * 64 * 4) + int(fr.numel()) + int(ins.numel())
+                if world > 1:
+                    dist.all_reduce(ti, op=dist.ReduceOp.MAX)
+                img_in = {"value": round(total / ti.item(), 1), "unit": "RoIs/s", "ms_per_batch": round(ti.item() * 1e3, 3),
+                          "h2d_bytes_per_step": (int(frames_h.numel()) + int(inst_h.numel())) * world, "frames_per_batch": Mf * world,
+                          "api": "givepose_b200.roi.posenet_inputs_from_detections (uint8 640x480 frames + instance maps from pinned host memory, "
+                                 "crops on the device) -> PoseNet.forward -> poses to the host",
+                          "roi_crop": {"ms": round(crop_ms, 3), "algorithmic_bytes": crop_bytes, "achieved_GBps": round(crop_bytes / crop_ms / 1e6, 1),
+                                       "bound": "hbm", "host_affine_ms": round(host_affine_ms, 3),
+                                       "note": "gp_roi_crop for the rank's whole batch (CUDA events); host_affine_ms = the per-RoI 6x6 solves in double on one host core"}}
+                del fr, ins, frames_h, inst_h
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -244,6 +304,8 @@ def run_posenet(args, rank, world, dev, dist):
                          "h2d_bytes_per_step": sum(nb(v) for v in host.values()) * world,
                          "d2h_bytes_per_step": sum(nb(x) for x in pose) * world,
                          "api": "givepose_b200.posenet.PoseNet.forward(data on pinned host memory, device)"}}
+        if img_in is not None:
+            entry["e2e_image_in"] = img_in
         if prec == "bf16":
             peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
             peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1383.2) if os.path.exists(peaks_path) else 1383.2

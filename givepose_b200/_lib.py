@@ -55,6 +55,8 @@ EXPORTS = {
     "gp_upsample_bilinear2x_backward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "gp_maxpool3x3s2": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "gp_pose_decode": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, ctypes.c_float, _VP]),
+    "gp_roi_affine_inverse": (_I, [_VP, _VP, _I, _I, _VP]),
+    "gp_roi_crop": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "gp_set_tuning": (_I, [_I, _I, _I, _I]),
     "gp_launch_count": (ctypes.c_uint64, []),
     "gp_launch_count_reset": (None, []),

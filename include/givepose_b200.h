@@ -173,6 +173,24 @@ int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_
                              const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
                              int dtype, void *stream);
 
+/* ---- RoI input pipeline in front of PoseNet.forward -------------------------------------------
+ * Replaces the per-RoI host work of the reference's loaders (evaluation/load_data_eval.py:256-289,
+ * datasets/load_data_nocs.py:277-305): crop_resize_by_warp_affine (tools/dataset_utils.py:101-114 = get_affine_transform
+ * :116-157 + cv2.warpAffine INTER_NEAREST), the (x/255 - mean)/std normalisation + HWC->CHW, and the crop of
+ * get_2d_coord_np (:8-30).  Index work: bit-exact against OpenCV 4.8's warpAffine (the reference's pin).
+ *
+ * gp_roi_affine_inverse (HOST, synchronous): for each RoI the 2x3 matrix cv2.getAffineTransform returns for the reference's
+ *   three float32 point pairs, inverted the way cv::warpAffine inverts it; center (B,2), scale (B,) double (bbox_center,
+ *   img_scale of the loaders); minv (B,6) double, dst -> src.
+ * gp_roi_crop: images (n_images,H,W,3) uint8 RGB, masks (n_masks,H,W) uint8, image_index / mask_index / inst_id (B,) int32
+ *   (inst_id < 0: roi_mask = float(mask); else roi_mask = (mask == inst_id)), minv_img / minv_out (B,6) double DEVICE pointers for
+ *   the img_size and out_res outputs, lut [3][256] fp32 = float((v/255.0 - mean[c])/std[c]) computed in double;
+ *   roi_img (B,3,S,S), roi_mask (B,1,S,S), roi_coord_2d (B,2,R,R) fp32 -- any of the three may be NULL.  B <= 65535. */
+int gp_roi_affine_inverse(const double *center, const double *scale, int B, int out_size, double *minv);
+int gp_roi_crop(const uint8_t *images, int n_images, int H, int W, const int *image_index, const uint8_t *masks, int n_masks,
+                const int *mask_index, const int *inst_id, const double *minv_img, const double *minv_out, const float *lut,
+                float *roi_img, float *roi_mask, float *roi_coord_2d, int B, int img_size, int out_res, void *stream);
+
 /* Dense layer on the tcgen05 tensor cores: y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]), x / w / y bf16 row-major, bias fp32,
  * fp32 accumulation in TMEM, bias + activation in the epilogue (act: 0 none, 1 LeakyReLU(slope), 2 ReLU).  The shape of
  * every Linear / 1x1 convolution of the heads: DCNv3 input_proj / output_proj / offset / mask (modules/dcnv3.py:325-354),
