@@ -43,6 +43,7 @@ EXPORTS = {
     "gp_dwconv3x3_ln_gelu": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _I, _VP]),
     "gp_small_k_linear": (_I, [_VP, _VP, _VP, _VP, ctypes.c_longlong, _I, _I, _I, _VP]),
     "gp_smallk_dwconv3x3_ln_gelu": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _I, _VP]),
+    "gp_dcnv3_smallk_fused": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _DP, _I, _I, _I, _VP]),
     "gp_groupnorm_workspace_floats": (_SZ, [_I, _I, _I, _I]),
     "gp_groupnorm_act": (_I, [_VP, _VP, _VP, _SZ, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _VP]),
     "gp_groupnorm_backward_workspace_floats": (_SZ, [_I, _I, _I, _I, _I]),

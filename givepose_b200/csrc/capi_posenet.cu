@@ -135,6 +135,35 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, 
     return (int)cudaGetLastError();
 }
 
+int gp_dcnv3_smallk_fused(const void *x, const void *offset, const void *mask_logits, const float *w2, const float *bias, void *out,
+                          size_t offset_elems, size_t mask_elems, const gp_dcnv3_desc *d, int K, int C_out, int dtype, void *stream) {
+    if (!x || !offset || !mask_logits || !w2 || !bias || !out || !d) return GP_ERR_NULL;
+    if (K != 3 || C_out != 256 || d->G != 4 || d->kh != 3 || d->kw != 3 || d->remove_center) return GP_ERR_UNSUPPORTED;
+    if (d->N <= 0 || d->H <= 0 || d->W <= 0 || d->sh <= 0 || d->sw <= 0 || d->dh <= 0 || d->dw <= 0) return GP_ERR_SHAPE;
+    if (d->Ho != gp_dcnv3_out_size(d->H, d->kh, d->sh, d->ph, d->dh) || d->Wo != gp_dcnv3_out_size(d->W, d->kw, d->sw, d->pw, d->dw)) return GP_ERR_SHAPE;
+    const long long n_pix = (long long)d->N * d->Ho * d->Wo;
+    if (offset_elems < (size_t)n_pix * 4 * 9 * 2 || mask_elems < (size_t)n_pix * 4 * 9) return GP_ERR_SHAPE;   // flat-prefix addressing
+    if (!al16(out) || !al16(w2) || (reinterpret_cast<uintptr_t>(offset) & 7u)) return GP_ERR_ALIGN;
+    if (n_pix == 0) return GP_OK;
+    SmallKFusedParams p;
+    p.H = d->H; p.W = d->W; p.Ho = d->Ho; p.Wo = d->Wo; p.sh = d->sh; p.sw = d->sw; p.dh = d->dh; p.dw = d->dw;
+    p.half_h = (d->dh * (d->kh - 1)) >> 1; p.half_w = (d->dw * (d->kw - 1)) >> 1;
+    p.base_h = p.half_h - d->ph; p.base_w = p.half_w - d->pw;
+    p.scale = d->offset_scale; p.n_pix = n_pix;
+    constexpr int PX = 4;
+    const long long want = (n_pix + 8 * PX - 1) / (8 * PX);
+    const unsigned grid = (unsigned)(want < 148ll * 2 ? want : 148ll * 2);   // 2 CTAs / SM (99 registers), persistent over pixel groups
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (dtype) {
+        case GP_F32: dcnv3_smallk_fused_kernel<float, PX><<<grid, 256, 0, st>>>((const float *)x, (const float *)offset, (const float *)mask_logits, w2, bias, (float *)out, p); break;
+        case GP_BF16: dcnv3_smallk_fused_kernel<__nv_bfloat16, PX><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (const __nv_bfloat16 *)offset, (const __nv_bfloat16 *)mask_logits, w2, bias, (__nv_bfloat16 *)out, p); break;
+        case GP_F16: dcnv3_smallk_fused_kernel<__half, PX><<<grid, 256, 0, st>>>((const __half *)x, (const __half *)offset, (const __half *)mask_logits, w2, bias, (__half *)out, p); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 size_t gp_groupnorm_backward_workspace_floats(int N, int H, int W, int C, int G) {
     if (N <= 0 || H <= 0 || W <= 0 || C <= 0 || G <= 0) return 0;
     int ppc = 0;

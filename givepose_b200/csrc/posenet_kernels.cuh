@@ -266,6 +266,135 @@ smallk_dwconv_ln_gelu_kernel(const T *__restrict__ x /*(N,H,W,K)*/, const float 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// First MAPEncoder layer, whole DCNv3 module in one kernel (conv_pnp_net.py:259-272, modules/dcnv3.py:318-356).
+// The module is  output_proj( core( input_proj(conv1x1(x)), offset, softmax(mask) ) )  with x the K = 3 channel NOCS map.
+// conv1x1, input_proj and output_proj are linear and the core is linear in its input, so for output pixel q
+//   core[q, g, c] = sum_j Wp[g*gc+c, j] * S[q,g,j] + bp[g*gc+c] * S0[q,g]
+//   S[q,g,j] = sum_p m_p sum_{corners k inside} w_k x[corner_k, j]      S0[q,g] = sum_p m_p sum_{corners k inside} w_k
+// (Wp, bp = input_proj o conv1x1; a corner outside the image contributes neither pixel value nor bias, cuh:55-75), hence
+//   out[q, :] = W2^T (S[q,0,0..2], S0[q,0], ..., S[q,G-1,0..2], S0[q,G-1]) + b_out,  W2 [G*(K+1)][C] composed on the host in fp64.
+// The C-channel input_proj tensor (2.1 GB per 1024 RoIs), the core output and the output_proj GEMM disappear; the sampling
+// arithmetic per (pixel, group, point) is locate() -- the same function the tiled sampler and the index hook use.
+// One warp = PX output pixels per iteration: phase 1 lane-linear over the PX*G*P (pixel, group, point) triples (partial sums
+// in shared memory), phase 2 the G*(K+1) sums per pixel, phase 3 the [G*(K+1)] x C map, lane = C/32 consecutive channels.
+// ---------------------------------------------------------------------------------------------------
+struct SmallKFusedParams {
+    int H, W, Ho, Wo, sh, sw, dh, dw, base_h, base_w, half_h, half_w;
+    float scale;
+    long long n_pix;   // N*Ho*Wo
+};
+
+template <typename T, int PX>
+__global__ void __launch_bounds__(256)
+dcnv3_smallk_fused_kernel(const T *__restrict__ x /*(N,H,W,3)*/, const T *__restrict__ off, const T *__restrict__ msk /*logits*/,
+                          const float *__restrict__ w2 /*[16][256]*/, const float *__restrict__ bias /*[256]*/, T *__restrict__ out,
+                          const __grid_constant__ SmallKFusedParams p) {
+    constexpr int G = 4, P = 9, K = 3, NS = G * (K + 1), C = 256, CPL = C / 32, NT = PX * G * P;
+    __shared__ __align__(16) float s_w2[NS * C];
+    __shared__ float s_part[8][PX * G * P][K + 2];   // per warp: (sum e w v_j, sum e w, e) per triple
+    __shared__ float s_S[8][PX][NS];
+    for (int i = threadIdx.x; i < NS * C; i += blockDim.x) s_w2[i] = w2[i];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float bs[CPL];
+#pragma unroll
+    for (int k = 0; k < CPL; ++k) bs[k] = __ldg(bias + CPL * lane + k);
+    const long long n_groups = (p.n_pix + PX - 1) / PX;
+    const long long HoWo = (long long)p.Ho * p.Wo;
+    for (long long grp = (long long)blockIdx.x * 8 + warp; grp < n_groups; grp += (long long)gridDim.x * 8) {
+        const long long q0 = grp * PX;
+        // ---- phase 1: one (pixel, group, point) triple per lane per pass
+        for (int t = lane; t < NT; t += 32) {
+            const int pix = t / (G * P), rem = t - pix * (G * P), g = rem / P, pt = rem - g * P;
+            const long long q = q0 + pix;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, e = 0.f;
+            if (q < p.n_pix) {
+                const long long b = q / HoWo;
+                const int r = (int)(q - b * HoWo), oh = r / p.Wo, ow = r - oh * p.Wo;
+                const long long row = (q * G + g) * P;   // flat (q*G+g)*P addressing, cuh:243-244
+                const T *mrow = msk + row;
+                float mx = to_acc<T>(__ldg(mrow));
+#pragma unroll
+                for (int i = 1; i < P; ++i) mx = fmaxf(mx, to_acc<T>(__ldg(mrow + i)));
+                e = expf(to_acc<T>(__ldg(mrow + pt)) - mx);   // softmax numerator; the denominator is summed in phase 2
+                float ox, oy;
+                load_pair<T>(off + 2 * (row + pt), ox, oy);
+                const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
+                const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
+                const int i = pt / 3, j = pt - 3 * i;   // p = i*kh + j, kernel WIDTH index slow (cuh:257-258)
+                Point<float> sp;
+                locate<float>(sp, p0_h_, p0_w_, j * p.dh, i * p.dw, ox, oy, p.scale, p.H, p.W);
+                if (sp.flags & F_IN) {
+                    const T *img = x + (b * p.H * p.W) * K;
+                    const float w1 = sp.hh * sp.hw, w2_ = sp.hh * sp.lw, w3 = sp.lh * sp.hw, w4 = sp.lh * sp.lw;
+                    auto corner = [&](unsigned flag, int yy, int xx, float w) {
+                        if (sp.flags & flag) {
+                            const T *px = img + ((long long)yy * p.W + xx) * K;
+                            a0 = fmaf(w, to_acc<T>(__ldg(px)), a0);
+                            a1 = fmaf(w, to_acc<T>(__ldg(px + 1)), a1);
+                            a2 = fmaf(w, to_acc<T>(__ldg(px + 2)), a2);
+                            a3 += w;
+                        }
+                    };
+                    corner(F_C1, sp.h_low, sp.w_low, w1);
+                    corner(F_C2, sp.h_low, sp.w_low + 1, w2_);
+                    corner(F_C3, sp.h_low + 1, sp.w_low, w3);
+                    corner(F_C4, sp.h_low + 1, sp.w_low + 1, w4);
+                }
+            }
+            float *sp_ = s_part[warp][t];
+            sp_[0] = e * a0; sp_[1] = e * a1; sp_[2] = e * a2; sp_[3] = e * a3; sp_[4] = e;
+        }
+        __syncwarp();
+        // ---- phase 2: the NS sums of each pixel, normalised by the softmax denominator of their group
+        for (int t = lane; t < PX * NS; t += 32) {
+            const int pix = t / NS, s = t - pix * NS, g = s >> 2, jj = s & 3;
+            const float(*pp)[K + 2] = &s_part[warp][(pix * G + g) * P];
+            float num = 0.f, den = 0.f;
+#pragma unroll
+            for (int k = 0; k < P; ++k) {
+                num += pp[k][jj];
+                den += pp[k][4];
+            }
+            s_S[warp][pix][s] = den > 0.f ? num / den : 0.f;   // den == 0 only for pixels past n_pix
+        }
+        __syncwarp();
+        // ---- phase 3: out[q, c] = b[c] + sum_s S[q,s] W2[s][c] for the lane's CPL channels of the PX pixels
+        float acc[PX][CPL];
+#pragma unroll
+        for (int px = 0; px < PX; ++px)
+#pragma unroll
+            for (int k = 0; k < CPL; ++k) acc[px][k] = bs[k];
+#pragma unroll
+        for (int s = 0; s < NS; ++s) {
+            float w[CPL];
+#pragma unroll
+            for (int k4 = 0; k4 < CPL; k4 += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&s_w2[s * C + CPL * lane + k4]);
+                w[k4] = v.x; w[k4 + 1] = v.y; w[k4 + 2] = v.z; w[k4 + 3] = v.w;
+            }
+#pragma unroll
+            for (int px = 0; px < PX; ++px) {
+                const float sv = s_S[warp][px][s];
+#pragma unroll
+                for (int k = 0; k < CPL; ++k) acc[px][k] = fmaf(sv, w[k], acc[px][k]);
+            }
+        }
+#pragma unroll
+        for (int px = 0; px < PX; ++px) {
+            const long long q = q0 + px;
+            if (q < p.n_pix) {
+                constexpr int V = 16 / (int)sizeof(T);
+#pragma unroll
+                for (int k = 0; k < CPL; k += V)
+                    Vec<T, V>::store_stream(out + q * C + CPL * lane + k, *reinterpret_cast<float(*)[V]>(&acc[px][k]));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // GroupNorm on channel-last activations (N, HW, C), G groups of cg = C/G channels.
 //   pass 1 (gn_stats): one CTA per (n, slab of pixels): per-group partial sum / sum of squares in fp32, written to
 //           partial[n][slab][g][2]; gn_finalize turns them into (mean, rstd) per (n, g).  No atomics anywhere: sums are taken

@@ -86,6 +86,34 @@ def smallk_dwconv3x3_ln_gelu(x, w_eff, bias, ln_w, ln_b, rows=None, eps=1e-6):
     return out
 
 
+def dcnv3_smallk_fused(x, offset, mask_logits, w2, bias, geom, remove_center=0):
+    """The whole first-layer DCNv3 module (``include/givepose_b200.h``, ``gp_dcnv3_smallk_fused``): ``x`` (N,H,W,3) channel-last,
+    ``offset`` / ``mask_logits`` flat-prefix buffers, ``w2`` (G*4, 256) / ``bias`` (256,) fp32 composed weights, ``geom`` the
+    11-tuple ``(kh, kw, sh, sw, ph, pw, dh, dw, group, group_channels, offset_scale)``; returns (N,Ho,Wo,256)."""
+    from ._lib import DCNv3Desc
+    _need_cuda("input", x)
+    _need_cuda("offset", offset, x.dtype)
+    _need_cuda("mask", mask_logits, x.dtype)
+    _need_cuda("w2", w2, torch.float32)
+    _need_cuda("bias", bias, torch.float32)
+    dt = _DTYPES.get(x.dtype)
+    if dt is None or x.dim() != 4:
+        raise RuntimeError(f"dcnv3_smallk_fused: unsupported input {x.dtype} {tuple(x.shape)}")
+    kh, kw, sh, sw, ph, pw, dh, dw, G, gc, scale = geom
+    N, H, W, K = x.shape
+    Ho = lib.gp_dcnv3_out_size(H, kh, sh, ph, dh)
+    Wo = lib.gp_dcnv3_out_size(W, kw, sw, pw, dw)
+    C = bias.numel()
+    if tuple(w2.shape) != (G * (K + 1), C):
+        raise RuntimeError(f"dcnv3_smallk_fused: w2 must be ({G * (K + 1)}, {C}), got {tuple(w2.shape)}")
+    d = DCNv3Desc(N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, int(bool(remove_center)), Ho, Wo, float(scale))
+    out = torch.empty((N, Ho, Wo, C), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_dcnv3_smallk_fused(_vp(x), _vp(offset), _vp(mask_logits), _vp(w2), _vp(bias), _vp(out), offset.numel(), mask_logits.numel(),
+                                        ctypes.byref(d), K, C, dt, _stream(x)), "dcnv3_smallk_fused")
+    return out
+
+
 def _nhwc(name, x):
     _need_cuda(name, x)
     dt = _DTYPES.get(x.dtype)

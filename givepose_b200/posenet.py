@@ -140,6 +140,7 @@ class DCNv3(nn.Module):
         self.output_proj = nn.Linear(channels, channels)
         self._reset_parameters()
         self._cache = {}
+        self.fuse_whole_module = True   # first-layer (K = 3) inference path: ops.dcnv3_smallk_fused
 
     def _reset_parameters(self):   # modules/dcnv3.py:308-316
         for m in (self.offset, self.mask):
@@ -183,7 +184,8 @@ class DCNv3(nn.Module):
         """``conv`` (1x1, K -> C) feeds this module and both of its consumers are linear in its output: compose
         ``input_proj o conv`` and ``dw_conv o conv`` (fp64 products, stored fp32); see ``include/givepose_b200.h``."""
         dw, ln = self.dw_conv[0], self.dw_conv[1][1]
-        ps = (conv.weight, conv.bias, self.input_proj.weight, self.input_proj.bias, dw.weight, dw.bias, ln.weight, ln.bias)
+        ps = (conv.weight, conv.bias, self.input_proj.weight, self.input_proj.bias, dw.weight, dw.bias, ln.weight, ln.bias,
+              self.output_proj.weight, self.output_proj.bias)
         key = (conv.weight.device,) + tuple(p._version for p in ps)
         if self._cache.get("ckey") != key:
             with torch.no_grad():
@@ -191,6 +193,14 @@ class DCNv3(nn.Module):
                 Wip, bip = self.input_proj.weight.detach().double(), self.input_proj.bias.detach().double()
                 wdw = dw.weight.detach().double().reshape(self.channels, 9)                              # (C, 9), tap = ky*3+kx
                 w_eff = torch.cat([wdw.t()[:, None, :] * Wc.t()[None, :, :], (wdw * bc[:, None]).t()[:, None, :]], dim=1)
+                # whole-module composition (ops.dcnv3_smallk_fused): out = W2^T [S_g,j ; S0_g] + b_out
+                Wp, bp = Wip @ Wc, Wip @ bc + bip                                                        # (C,K), (C,)
+                Wo, G, gc = self.output_proj.weight.detach().double(), self.group, self.group_channels
+                WoG = Wo.reshape(Wo.shape[0], G, gc)                                                     # (O, G, gc)
+                w2 = torch.cat([torch.einsum("ogc,gcj->gjo", WoG, Wp.reshape(G, gc, -1)),
+                                torch.einsum("ogc,gc->go", WoG, bp.reshape(G, gc))[:, None, :]], dim=1)  # (G, K+1, O)
+                self._cache.update({"w2": w2.reshape(G * (Wc.shape[1] + 1), -1).float().contiguous(),
+                                    "b_out": self.output_proj.bias.detach().float().contiguous()})
                 self._cache.update({"ckey": key, "wp_t": (Wip @ Wc).t().float().contiguous(), "bp": (Wip @ bc + bip).float().contiguous(),
                                     "w_eff": w_eff.float().contiguous(), "dw_b": dw.bias.detach().float().contiguous(),
                                     "cln_w": ln.weight.detach().float().contiguous(), "cln_b": ln.bias.detach().float().contiguous()})
@@ -206,8 +216,13 @@ class DCNv3(nn.Module):
         rows = min(N * Ho * Wo, N * H * W)
         c = self._composed_params(conv)
         x_small = x_small.contiguous()
-        x = ops.small_k_linear(x_small, c["wp_t"], c["bp"])
         x1 = ops.smallk_dwconv3x3_ln_gelu(x_small, c["w_eff"], c["dw_b"], c["cln_w"], c["cln_b"], rows, eps=1e-6)
+        if self.fuse_whole_module and self.group == 4 and self.kernel_size == 3 and not self.remove_center and self.channels == 256:
+            # input_proj, the core and output_proj collapse into one sampling kernel over the 3-channel map + a 16 -> 256 map:
+            # the 256-channel input_proj tensor is never written
+            return ops.dcnv3_smallk_fused(x_small, _lin(x1, self.offset).contiguous(), _lin(x1, self.mask).contiguous(), c["w2"], c["b_out"],
+                                          self._geom(), self.remove_center)
+        x = ops.small_k_linear(x_small, c["wp_t"], c["bp"])
         return self._sample(x, x1)
 
     def forward(self, input):

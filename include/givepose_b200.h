@@ -147,6 +147,17 @@ int gp_small_k_linear(const void *x, const float *w_t, const float *bias, void *
 int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *bias, const float *ln_w, const float *ln_b,
                                 void *out, int N, int H, int W, int K, int C, long long rows, float eps, int dtype, void *stream);
 
+/* The whole first-layer DCNv3 module in one kernel: out = output_proj(core(input_proj(conv1x1(x)), offset, softmax(mask)))
+ * for the K = 3 channel input of MAPEncoder's first DCNv3_C (conv_pnp_net.py:259-272, network/dcnv3.py:32-38,
+ * modules/dcnv3.py:318-356).  All three projections are linear and the core is linear in its input, so the kernel samples the
+ * K-channel map itself (K values + the sum of the in-image weights per (pixel, group)) and applies ONE composed
+ * [G*(K+1)] -> C_out map: w2[(g*(K+1)+j)*C_out + o] = sum_c Wo[o, g*gc+c] * Wp[g*gc+c, j] (j < K), j == K: the same with bp
+ * (Wp, bp = input_proj o conv1x1), bias = output_proj bias; composed by the caller in fp64, stored fp32.
+ * x (N,H,W,K), offset / mask_logits: the flat [N*Ho*Wo*G*P] prefix is read (cuh:243-244), softmax over P fused;
+ * out (N,Ho,Wo,C_out).  Indices / bounds are those of gp_dcnv3_forward (same locate()).  Supported: K 3, G 4, 3x3, C_out 256. */
+int gp_dcnv3_smallk_fused(const void *x, const void *offset, const void *mask_logits, const float *w2, const float *bias, void *out,
+                          size_t offset_elems, size_t mask_elems, const gp_dcnv3_desc *d, int K, int C_out, int dtype, void *stream);
+
 /* y = act(GroupNorm_G(x)) on channel-last (N,H,W,C) activations (layer_utils.py:32-60 "GN", conv_module.py order
  * conv -> norm -> act); act: 0 none, 1 ReLU, 2 GELU.  stats: scratch of at least gp_groupnorm_workspace_floats(N,H,W,G)
  * floats (no need to clear it).  Sums are taken in a fixed order (no atomics): results are bit-reproducible. */

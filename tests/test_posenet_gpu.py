@@ -474,3 +474,24 @@ def test_upsample2x_autograd_matches_torch(shape, dtype, tol):
     for a, b, name in ((y.detach(), yr.detach(), "y"), (xa.grad, xr.grad, "dx")):
         err = ((a.float() - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
         assert err < tol, (name, err)
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 2e-2)], ids=["f32", "bf16"])
+def test_first_layer_whole_module_fusion_equals_the_unfused_module(OP, dtype, tol):
+    """ops.dcnv3_smallk_fused (input_proj, core, output_proj of the K = 3 first MAPEncoder layer collapsed into a sampling
+    kernel over the 3-channel map + a composed 16 -> 256 map) against the unfused inference path (small_k_linear ->
+    tiled sampler -> output_proj GEMM) on the same module, O(1) weights with pixel-scale offsets; N = 8 covers the
+    flat-prefix batch coupling (RoI b reads the offset rows of RoI b // 4)."""
+    _, net = build(OP, "o1", precision="fp32" if dtype == torch.float32 else "bf16")
+    layer = net.nocs_encoder.features[0]
+    g = torch.Generator().manual_seed(21)
+    x = (torch.rand(8, 64, 64, 3, generator=g) - 0.5).to(dtype).cuda()
+    with torch.no_grad():
+        layer.dcnv3.fuse_whole_module = True
+        fused = layer.forward_nhwc(x)
+        layer.dcnv3.fuse_whole_module = False
+        plain = layer.forward_nhwc(x)
+        layer.dcnv3.fuse_whole_module = True
+    assert fused.shape == plain.shape == (8, 32, 32, 256) and fused.dtype == dtype
+    err = ((fused.float() - plain.float()).abs().max() / plain.float().abs().max()).item()
+    assert err < tol, err
