@@ -401,6 +401,23 @@ def run_reference(args, rank):
         "e2e": {"value": round(gbps, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if torch.cuda.is_available():
+        # informational: the reference's own CUDA kernels on this GPU (the line's value stays the CPU path the contract asks for)
+        dev = torch.device("cuda", 0)
+        inp, off, m, gout = make_inputs(CFG["N"], args.dist, torch.float32, dev, seed=3)
+
+        def timed(fn, reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+        rc = time_reference_cuda(inp, off, m, gout, "f32", timed, 10, float("nan"), float("nan"))
+        line["reference_cuda_kernels"] = {k: v for k, v in rc.items() if not k.startswith(("ours", "speedup"))}
+        del inp, off, m, gout
     if not args.no_posenet:
         rps, dtp, th = time_posenet_cpu(8, max(1, min(args.steps, 3)))
         line["posenet"] = {"metric": "posenet_inference_rois_per_s", "value": round(rps, 3), "unit": "RoIs/s", "dtype": "f32",

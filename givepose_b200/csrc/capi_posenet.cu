@@ -152,7 +152,7 @@ int gp_dcnv3_smallk_fused(const void *x, const void *offset, const void *mask_lo
     p.scale = d->offset_scale; p.n_pix = n_pix;
     constexpr int PX = 4;
     const long long want = (n_pix + 8 * PX - 1) / (8 * PX);
-    const unsigned grid = (unsigned)(want < 148ll * 2 ? want : 148ll * 2);   // 2 CTAs / SM (99 registers), persistent over pixel groups
+    const unsigned grid = (unsigned)(want < 148ll * 3 ? want : 148ll * 3);   // 3 CTAs / SM (launch bounds), persistent over pixel groups
     cudaStream_t st = (cudaStream_t)stream;
     switch (dtype) {
         case GP_F32: dcnv3_smallk_fused_kernel<float, PX><<<grid, 256, 0, st>>>((const float *)x, (const float *)offset, (const float *)mask_logits, w2, bias, (float *)out, p); break;

@@ -285,7 +285,7 @@ struct SmallKFusedParams {
 };
 
 template <typename T, int PX>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 dcnv3_smallk_fused_kernel(const T *__restrict__ x /*(N,H,W,3)*/, const T *__restrict__ off, const T *__restrict__ msk /*logits*/,
                           const float *__restrict__ w2 /*[16][256]*/, const float *__restrict__ bias /*[256]*/, T *__restrict__ out,
                           const __grid_constant__ SmallKFusedParams p) {

@@ -155,3 +155,38 @@ def test_error_behaviour_matches_the_reference_extension(ops, ref):
             impl.dcnv3_forward(inp, off, m, *args, 4, 0)            # 6 % min(6, 4) != 0
         with pytest.raises(RuntimeError):
             impl.dcnv3_forward(inp, off, m, *args[:8], 2, 15, 1.0, 256, 0)   # C != G*gc
+
+
+SWEEP = [
+    # (N, H, W, G, gc, k, stride, pad, dil, scale, remove_center, dist)
+    (2, 17, 23, 2, 32, 3, 1, 1, 1, 1.0, 0, "T"),
+    (2, 17, 23, 2, 32, 3, 1, 1, 2, 1.0, 0, "T"),      # dilation 2
+    (2, 16, 16, 4, 16, 5, 1, 2, 1, 0.5, 0, "T"),      # 5x5, offset_scale 0.5
+    (2, 16, 16, 4, 16, 5, 1, 2, 1, 2.0, 1, "M"),      # 5x5 without its centre
+    (3, 21, 13, 1, 64, 3, 2, 1, 1, 1.0, 0, "M"),      # stride 2, odd sizes, one group
+    (4, 12, 12, 8, 8, 3, 1, 0, 1, 1.0, 0, "T"),       # no padding: out 10x10
+    (2, 9, 31, 3, 24, 3, 3, 1, 1, 1.3, 1, "T"),       # stride 3, gc 24 (generic kernels)
+    (1, 64, 64, 8, 32, 3, 1, 1, 1, 4.0, 0, "T"),      # offsets up to 40 px: most samples leave the image
+    (5, 8, 8, 2, 128, 3, 1, 1, 1, 1.0, 0, "M"),       # wide groups
+    (2, 33, 33, 4, 64, 1, 1, 0, 1, 1.0, 0, "M"),      # 1x1 kernel: one sampling point
+]
+
+
+@pytest.mark.parametrize("cfg", SWEEP, ids=[f"N{c[0]}_{c[1]}x{c[2]}_G{c[3]}x{c[4]}_k{c[5]}s{c[6]}p{c[7]}d{c[8]}_sc{c[9]}_rc{c[10]}_{c[11]}" for c in SWEEP])
+@pytest.mark.parametrize("dtype,ftol,gtol", [(torch.float64, 1e-12, 1e-10), (torch.float32, 1e-5, 1e-4), (torch.float16, 2e-3, 5e-3)],
+                         ids=["f64", "f32", "f16"])
+def test_geometry_sweep_vs_reference_kernels(ops, ref, cfg, dtype, ftol, gtol):
+    """Kernel size / stride / padding / dilation / offset_scale / remove_center / group shapes the golden file does not hold,
+    in every dtype the reference dispatches (dcnv3_cuda.cu:69: double, float, half), against the reference's own kernels."""
+    N, H, W, G, gc, k, s, pad, dil, scale, rc, dist = cfg
+    if rc and k == 1:
+        pytest.skip("remove_center needs more than one point")
+    P = k * k - rc
+    Ho = (H + 2 * pad - (dil * (k - 1) + 1)) // s + 1
+    Wo = (W + 2 * pad - (dil * (k - 1) + 1)) // s + 1
+    inp, off, m, gout = _inputs(N, H, W, G, gc, P, Ho, Wo, dist, dtype, seed=11)
+    args = (k, k, s, s, pad, pad, dil, dil, G, gc, scale)
+    out, rout, grads, rgrads = _both(ops, ref, inp, off, m, gout, args, rc=rc)
+    assert out.shape == rout.shape == (N, Ho, Wo, G * gc) and _rel(out, rout) < ftol
+    for got, want, name in zip(grads, rgrads, ("grad_input", "grad_offset", "grad_mask")):
+        assert got.shape == want.shape and _rel(got, want) < gtol, name

@@ -37,7 +37,11 @@ KEYS = [
 
 
 def raw(rep):
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    """Rows of a report: from the .ncu-rep if it came back, else from the `--page raw --csv` export made on the GPU box."""
+    if os.path.exists(rep):
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        out = open(rep.replace(".ncu-rep", "_raw.csv")).read()
     rows = list(csv.reader(io.StringIO(out)))
     hdr, units = rows[0], rows[1]
     return [dict(zip(hdr, r)) for r in rows[2:]], dict(zip(hdr, units))
@@ -56,7 +60,7 @@ def main():
     traffic = {}
     for dt in ("f32", "bf16"):
         rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof_{dt}.ncu-rep")
-        if not os.path.exists(rep):
+        if not os.path.exists(rep) and not os.path.exists(rep.replace(".ncu-rep", "_raw.csv")):
             continue
         rows, units = raw(rep)
         out_md.append(f"\n## {dt}\n")
@@ -80,6 +84,46 @@ def main():
             if kind:
                 traffic[f"dcnv3_{kind}_{dt}_dram_bytes"] = int(to_bytes(r["dram__bytes_read.sum"], units["dram__bytes_read.sum"]) +
                                                               to_bytes(r["dram__bytes_write.sum"], units["dram__bytes_write.sum"]))
+    # other captures of the round: the tcgen05 dense layer (tensor-pipe evidence) and the kernels added this round
+    TC_KEYS = [("gpu__time_duration.sum", "duration"),
+               ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor pipe active % (of active cycles)"),
+               ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe active % (of elapsed cycles)"),
+               ("sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.sum", "tcgen05 (UTCHMMA) bf16->fp32 ops = 2*M*N*K"),
+               ("sm__ops_path_tensor_op_hmma_src_bf16_dst_fp32_sparsity_off.sum", "legacy mma.sync (HMMA) ops"),
+               ("sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor memory (TMEM) active %"),
+               ("dram__bytes_read.sum", "dram read"), ("dram__bytes_write.sum", "dram write"),
+               ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram throughput %peak"),
+               ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %peak"),
+               ("launch__registers_per_thread", "registers/thread"), ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %")]
+    for name, title, keys in (("tcl_mem", "tcgen05 dense layer, M=262144 N=256 K=256 (HBM-bound projection shape)", TC_KEYS),
+                              ("tcl_fc1", "tcgen05 dense layer, M=4096 N=2048 K=8192 (fc1||fc1_z, tensor-bound)", TC_KEYS),
+                              ("new", "kernels added in this round (tools/profile_target_r06.py)", KEYS)):
+        rep = os.path.join(ROOT, "gpurun_out", f"{tag}_prof_{name}.ncu-rep")
+        if not os.path.exists(rep) and not os.path.exists(rep.replace(".ncu-rep", "_raw.csv")):
+            continue
+        rows, units = raw(rep)
+        # keep the LAST launch of every distinct kernel (the first pays cold caches)
+        last = {}
+        for r in rows:
+            last[r["Kernel Name"].split("(")[0]] = r
+        rows = list(last.values())
+        out_md.append(f"\n## {title}\n")
+        names = [r["Kernel Name"].split("(")[0].replace("void gp::", "") for r in rows]
+        out_md.append("| metric | " + " | ".join(names) + " |")
+        out_md.append("|---|" + "---|" * len(rows))
+        tensor_keys = [k for k in rows[0] if "tensor" in k and ("pct_of_peak_sustained_active" in k or k.endswith(".sum"))][:0]
+        for key, label in keys:
+            if key not in rows[0]:
+                continue
+            vals = []
+            for r in rows:
+                v = r[key]
+                try:
+                    v = f"{float(v.replace(',', '')):,.4g}" if abs(float(v.replace(',', ''))) < 1e6 else f"{float(v.replace(',', '')):,.0f}"
+                except ValueError:
+                    pass
+                vals.append(f"{v} {units[key]}".strip())
+            out_md.append(f"| {label} (`{key}`) | " + " | ".join(vals) + " |")
     # launch list of the bench command
     lp = os.path.join(ROOT, "gpurun_out", f"{tag}_launches.csv")
     if os.path.exists(lp):
