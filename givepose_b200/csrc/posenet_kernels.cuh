@@ -538,6 +538,17 @@ gn_apply_kernel(const T *__restrict__ x, const float *__restrict__ stats, const 
 // ---------------------------------------------------------------------------------------------------
 template <typename T, int ACT> __device__ __forceinline__ float gn_act_grad(float z) {
     if (ACT == ACT_RELU) return z > 0.f ? 1.f : 0.f;
+    if (ACT == ACT_GELU && sizeof(T) == 2) {
+        // 16-bit storage: the derivative of exactly what the forward evaluates (gelu_fast16): g = 0.5 z (1 + tanh u),
+        // u = zc (a + b zc^2 + c zc^4), zc = clamp(z, +-6):  g' = 0.5 (1 + t) + 0.5 z (1 - t^2) u'(zc)   (u' = 0 where clamped)
+        const float zc = fminf(fmaxf(z, -6.f), 6.f);
+        const float z2 = zc * zc;
+        const float u = zc * fmaf(z2, fmaf(z2, -3.51523083e-4f, 3.70056758e-2f), 7.97507859e-1f);
+        const float du = fabsf(z) < 6.f ? fmaf(z2, fmaf(z2, 5.f * -3.51523083e-4f, 3.f * 3.70056758e-2f), 7.97507859e-1f) : 0.f;
+        float t;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+        return fmaf(0.5f * z * du, fmaf(-t, t, 1.f), fmaf(0.5f, t, 0.5f));
+    }
     if (ACT == ACT_GELU) {   // d/dz [z Phi(z)] = Phi(z) + z phi(z); erf as in gelu_erf (A&S 7.1.26), exp(-z^2/2) shared
         const float a = fabsf(z) * 0.70710678118654752440f;
         const float t = __frcp_rn(fmaf(0.3275911f, a, 1.f));
@@ -574,16 +585,29 @@ gn_bwd_stats_kernel(const T *__restrict__ x, const T *__restrict__ dy, const flo
             sc[k] = rstd[k] * __ldg(gamma + c);
             sh[k] = __ldg(beta + c) - mean[k] * sc[k];
         }
-        for (int p = p0 + prow; p < p1; p += pstep) {
-            float v[4], d[4];
+        for (int p = p0 + prow; p < p1; p += 2 * pstep) {   // two pixels in flight; sums stay in pixel order
+            const bool two = p + pstep < p1;
+            float v[4], d[4], v2[4], d2[4];
             const long long o = ((long long)n * HW + p) * C + 4 * cq;
             Vec4IO<T>::ld(x + o, v);
             Vec4IO<T>::ld(dy + o, d);
+            if (two) {
+                Vec4IO<T>::ld(x + o + (long long)pstep * C, v2);
+                Vec4IO<T>::ld(dy + o + (long long)pstep * C, d2);
+            }
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const float dz = d[k] * gn_act_grad<T, ACT>(fmaf(v[k], sc[k], sh[k]));
                 s1[k] += dz;
                 s2[k] = fmaf(dz, (v[k] - mean[k]) * rstd[k], s2[k]);
+            }
+            if (two) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float dz = d2[k] * gn_act_grad<T, ACT>(fmaf(v2[k], sc[k], sh[k]));
+                    s1[k] += dz;
+                    s2[k] = fmaf(dz, (v2[k] - mean[k]) * rstd[k], s2[k]);
+                }
             }
         }
     }
