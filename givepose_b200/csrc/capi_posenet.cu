@@ -238,6 +238,25 @@ int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, i
     if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y)) return GP_ERR_ALIGN;
     cudaStream_t st = (cudaStream_t)stream;
+    {   // column-strip kernel when the shape tiles exactly (the decoder: C = 256, Wo = 32 / 64)
+        const int V = dtype == GP_F32 ? 4 : 8, q = C / V;
+        if (q <= 256 && 256 % q == 0 && (2 * W) % (256 / q) == 0 && N <= 65535) {
+            const int cols = 256 / q, gx = 2 * W / cols, Ho = 2 * H;
+            int slabs = (int)((148ll * 16 + (long long)N * gx - 1) / ((long long)N * gx));   // >= 16 CTAs per SM worth of work
+            if (slabs > Ho / 4) slabs = Ho / 4 > 0 ? Ho / 4 : 1;                              // >= 4 rows per CTA
+            if (slabs < 1) slabs = 1;
+            const int rpc = (Ho + slabs - 1) / slabs;
+            const dim3 grid((unsigned)gx, (unsigned)((Ho + rpc - 1) / rpc), (unsigned)N);
+            switch (dtype) {
+                case GP_F32: upsample2x_strip_kernel<float><<<grid, 256, 0, st>>>((const float *)x, (float *)y, H, W, C, rpc); break;
+                case GP_BF16: upsample2x_strip_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, (__nv_bfloat16 *)y, H, W, C, rpc); break;
+                case GP_F16: upsample2x_strip_kernel<__half><<<grid, 256, 0, st>>>((const __half *)x, (__half *)y, H, W, C, rpc); break;
+                default: return GP_ERR_DTYPE;
+            }
+            count_launch();
+            return (int)cudaGetLastError();
+        }
+    }
     int ppc = 0;
     const dim3 grid = slab_grid(N, 4 * H * W, 16, &ppc);
     switch (dtype) {
