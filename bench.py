@@ -293,6 +293,26 @@ def run_posenet(args, rank, world, dev, dist):
                                        "bound": "hbm", "host_affine_ms": round(host_affine_ms, 3),
                                        "note": "gp_roi_crop for the rank's whole batch (CUDA events); host_affine_ms = the per-RoI 6x6 solves in double on one host core"}}
                 del fr, ins, frames_h, inst_h
+            # serving latency of one frame's detections (B = 8): eager vs the same forward as one CUDA graph
+            latency = None
+            if prec == "bf16" and rank == 0:
+                try:
+                    from givepose_b200.posenet import GraphedPoseNet
+                    small = {k: (v[:8] if (k != "cam_K" or v.dim() == 3) else v).contiguous() for k, v in resident.items()}
+                    gnet = GraphedPoseNet(net, small, dev)
+
+                    def lat(fn, reps=20):
+                        fn(); torch.cuda.synchronize()
+                        t0 = time.perf_counter()
+                        for _ in range(reps):
+                            r = fn()
+                            r["trans"].cpu()   # the pose leaves the device every call
+                        return (time.perf_counter() - t0) / reps * 1e3
+                    latency = {"rois": 8, "eager_ms": round(lat(lambda: net(small, dev)), 3), "graphed_ms": round(lat(lambda: gnet(small)), 3),
+                               "api": "givepose_b200.posenet.GraphedPoseNet (fixed-B forward as one CUDA graph), wall clock incl. D2H of trans"}
+                    del gnet
+                except Exception as e:
+                    latency = {"unavailable": f"{type(e).__name__}: {str(e)[:150]}"}
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -306,6 +326,8 @@ def run_posenet(args, rank, world, dev, dist):
                          "api": "givepose_b200.posenet.PoseNet.forward(data on pinned host memory, device)"}}
         if img_in is not None:
             entry["e2e_image_in"] = img_in
+        if latency is not None:
+            entry["latency_8_rois"] = latency
         if prec == "bf16":
             peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
             peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1383.2) if os.path.exists(peaks_path) else 1383.2

@@ -867,3 +867,44 @@ def _pose_decode_torch(rot6, t, cams, centers, whs, ratios, is_allo, eps=1e-4):
                          qy * Z - w * X, qx * Z - w * Y, qy * Z + w * X, 1 - (qx * X + qy * Y)], dim=1).reshape(-1, 3, 3)
         R = torch.matmul(M, R)
     return R, trans
+
+
+class GraphedPoseNet:
+    """``PoseNet.forward`` for a FIXED number of RoIs captured once as a CUDA graph and replayed (serving a frame's handful of
+    detections: at B = 8 the eager forward is ~300 kernel launches of a few microseconds each, i.e. launch-bound).
+    ``__call__(data)`` copies the inputs (host or device tensors, any subset of the keys may already be the static buffers)
+    into static device buffers on the current stream and replays; the returned tensors are the graph's static outputs --
+    consume or clone them before the next call.  ``rot`` stays on the device (one D2H of the caller's choice instead of the
+    reference's per-RoI host loop, ``pose_from_pred_centroid_z.py:139-157``)."""
+
+    KEYS = ("roi_img", "roi_mask", "roi_coord_2d", "cam_K", "mean_size", "roi_wh", "bbox_center", "resize_ratio")
+
+    def __init__(self, net: PoseNet, example: dict, device, warmup: int = 2):
+        dev = torch.device(device)
+        if net.training:
+            raise RuntimeError("GraphedPoseNet: call net.eval() first")
+        self.net, self.dev = net, dev
+        self.static = {k: example[k].to(dev).clone() for k in self.KEYS}
+        rot_on_cpu, net.cfg.rot_on_cpu = net.cfg.rot_on_cpu, False   # no D2H inside the capture
+        try:
+            with torch.no_grad():
+                side = torch.cuda.Stream(dev)
+                side.wait_stream(torch.cuda.current_stream(dev))
+                with torch.cuda.stream(side):
+                    for _ in range(max(1, warmup)):   # cuDNN algorithm selection, weight caches
+                        net(self.static, dev)
+                torch.cuda.current_stream(dev).wait_stream(side)
+                torch.cuda.synchronize(dev)
+                self.graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(self.graph):
+                    self.out = net(self.static, dev)
+        finally:
+            net.cfg.rot_on_cpu = rot_on_cpu
+
+    def __call__(self, data: dict) -> dict:
+        for k in self.KEYS:
+            v = data[k]
+            if v is not self.static[k]:
+                self.static[k].copy_(v, non_blocking=True)
+        self.graph.replay()
+        return self.out

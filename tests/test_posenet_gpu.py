@@ -495,3 +495,20 @@ def test_first_layer_whole_module_fusion_equals_the_unfused_module(OP, dtype, to
     assert fused.shape == plain.shape == (8, 32, 32, 256) and fused.dtype == dtype
     err = ((fused.float() - plain.float()).abs().max() / plain.float().abs().max()).item()
     assert err < tol, err
+
+
+def test_graphed_inference_equals_eager_forward(OP):
+    """GraphedPoseNet (fixed-B forward as one CUDA graph) returns what the eager forward returns, for the inputs it was
+    captured with and for new inputs copied into its static buffers; fp32 parity mode, so the match is exact."""
+    from givepose_b200.posenet import GraphedPoseNet
+    _, net = build(OP, "o1", precision="fp32")
+    d0 = {k: v.cuda() for k, v in OP.make_inputs(8, seed=3).items()}
+    d1 = OP.make_inputs(8, seed=4)                       # host tensors: copied into the static buffers
+    with torch.no_grad():
+        e0, e1 = net(d0, "cuda"), net({k: v.cuda() for k, v in d1.items()}, "cuda")
+        g = GraphedPoseNet(net, d0, "cuda")
+        for data, want in ((d0, e0), (d1, e1), (d0, e0)):
+            got = g(data)
+            for k in ("rot", "trans", "size", "nocs_coor", "ivfc_coor", "mask"):
+                assert got[k].is_cuda and torch.equal(got[k].cpu(), want[k].cpu()), k
+    assert net.cfg.rot_on_cpu   # restored
