@@ -131,6 +131,22 @@ def roi_crops(images: torch.Tensor, bbox_center, img_scale, image_index=0, masks
     return out
 
 
+def full_image_tensor(images: torch.Tensor, image_index=None, mean=IMG_MEAN, std=IMG_STD) -> torch.Tensor:
+    """``full_img`` of the loaders with ``FLAGS.resize_full`` off (``load_data_eval.py:345-347``, the input of ``Scale_net``):
+    ``(frame / 255.0 - mean) / std`` -> CHW float32, through the same double-precision table as the crops (bit-exact);
+    ``image_index`` (B,) repeats each frame for its RoIs like ``np.array([full_img] * len(roi_imgs))`` (``:348``)."""
+    if not images.is_cuda or images.dtype != torch.uint8 or images.shape[-1] != 3:
+        raise RuntimeError("full_image_tensor: images must be CUDA uint8 (M,H,W,3)")
+    if images.dim() == 3:
+        images = images[None]
+    lut = normalisation_table(mean, std).to(images.device)
+    idx = images.long()
+    out = torch.stack([lut[c][idx[..., c]] for c in range(3)], dim=1)            # (M,3,H,W)
+    if image_index is not None:
+        out = out[torch.as_tensor(image_index, dtype=torch.long, device=images.device)]
+    return out
+
+
 def posenet_inputs_from_detections(images: torch.Tensor, bboxes, masks: torch.Tensor, cam_K, mean_size, image_index=0, mask_index=None,
                                    inst_id=-1, img_size: int = 256, out_res: int = 64, pad_scale: float = 1.5) -> Dict[str, torch.Tensor]:
     """Frames + detections -> the complete input dict of ``PoseNet.forward`` (keys / shapes / dtypes of

@@ -99,3 +99,11 @@ def test_detections_to_posenet_forward(roi):
         ref_in.update({k: torch.from_numpy(np.stack([w[j] for w in want])) for j, k in enumerate(("roi_img", "roi_mask", "roi_coord_2d"))})
         ref = net(ref_in, "cuda")
     assert out["rot"].shape == (B, 3, 3) and torch.equal(out["rot"], ref["rot"]) and torch.equal(out["trans"], ref["trans"])
+
+
+def test_full_image_tensor_is_the_loaders_normalisation(roi):
+    rng = np.random.default_rng(4)
+    frames = rng.integers(0, 256, (2, 48, 64, 3), dtype=np.uint8)
+    got = roi.full_image_tensor(torch.from_numpy(frames).cuda(), image_index=[1, 0, 1]).cpu().numpy()
+    want = np.stack([((f / 255.0 - roi.IMG_MEAN) / roi.IMG_STD).transpose(2, 0, 1).astype(np.float32) for f in frames])[[1, 0, 1]]
+    assert got.shape == (3, 3, 48, 64) and np.array_equal(got, want)   # load_data_eval.py:346-348
