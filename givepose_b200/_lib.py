@@ -58,6 +58,7 @@ EXPORTS = {
     "gp_pose_decode": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, ctypes.c_float, _VP]),
     "gp_roi_affine_inverse": (_I, [_VP, _VP, _I, _I, _VP]),
     "gp_roi_crop": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "gp_resize_linear_u8_normalize": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "gp_set_tuning": (_I, [_I, _I, _I, _I]),
     "gp_launch_count": (ctypes.c_uint64, []),
     "gp_launch_count_reset": (None, []),

@@ -104,6 +104,49 @@ roi_crop_kernel(const uint8_t *__restrict__ images, int H, int W, const int *__r
     }
 }
 
+// cv2.resize(image, (dw, dh)) -- INTER_LINEAR on 8-bit pixels (load_data_eval.py:336, FLAGS.resize_full) -- followed by the
+// loaders' normalisation.  OpenCV's 8-bit linear resize is fixed point (resize.cpp, INTER_RESIZE_COEF_BITS = 11):
+//   fx = (float)((dx + 0.5) * scale_x - 0.5), sx = floor(fx), fx -= sx, clamped at the borders (fx = 0)
+//   alpha = { cvRound((1 - fx) * 2048), cvRound(fx * 2048) }  (float arithmetic, saturate_cast<short>), beta likewise for rows
+//   row[k] = S[sx] * alpha0 + S[sx + 1] * alpha1                                            (HResizeLinear, int)
+//   dst = (((beta0 * (row0 >> 4)) >> 16) + ((beta1 * (row1 >> 4)) >> 16) + 2) >> 2          (VResizeLinear<uchar>)
+// with scale_x = 1.0 / ((double)dw / W).  Bit-exact against cv2 for source sizes >= the output size (the frames of the loaders
+// are 480 x 640 -> 256 x 256); OpenCV takes a different path when upscaling (differences of 1 in ~0.1 % of the pixels), so the
+// host refuses H < dh or W < dw.  One thread per output pixel, three channels.
+__device__ __forceinline__ void resize_coeff(int d, double scale, int n_src, int &s, int &a0, int &a1) {
+    float f = (float)__dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+    s = (int)floorf(f);
+    f = __fsub_rn(f, (float)s);
+    if (s < 0) { f = 0.f; s = 0; }
+    if (s >= n_src - 1) { f = 0.f; s = n_src - 1; }
+    a0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+    a1 = __float2int_rn(__fmul_rn(f, 2048.f));
+}
+
+__global__ void __launch_bounds__(256)
+resize_linear_u8_norm_kernel(const uint8_t *__restrict__ images, const int *__restrict__ image_index, const float *__restrict__ lut,
+                             float *__restrict__ out, int H, int W, int dh, int dw, double scale_y, double scale_x) {
+    const int b = blockIdx.y;
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= dh * dw) return;
+    const int dy = p / dw, dx = p - dy * dw;
+    int sx, sy, a0, a1, b0, b1;
+    resize_coeff(dx, scale_x, W, sx, a0, a1);
+    resize_coeff(dy, scale_y, H, sy, b0, b1);
+    const int sx1 = min(sx + 1, W - 1), sy1 = min(sy + 1, H - 1);
+    const uint8_t *img = images + (long long)(image_index ? image_index[b] : b) * H * W * 3;
+    const uint8_t *r0 = img + (long long)sy * W * 3, *r1 = img + (long long)sy1 * W * 3;
+    float *o = out + (long long)b * 3 * dh * dw + p;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int row0 = r0[sx * 3 + c] * a0 + r0[sx1 * 3 + c] * a1;
+        const int row1 = r1[sx * 3 + c] * a0 + r1[sx1 * 3 + c] * a1;
+        int v = (((b0 * (row0 >> 4)) >> 16) + ((b1 * (row1 >> 4)) >> 16) + 2) >> 2;
+        v = max(0, min(255, v));
+        __stcs(o + (long long)c * dh * dw, __ldg(lut + 256 * c + v));
+    }
+}
+
 // ---- host: the affine the reference builds per RoI, in double, bit for bit -------------------------------------------
 // cv::LU (matrix_decomp.cpp LUImpl<double>): partial pivoting, elimination with alpha = A[j][i] * (-1/A[i][i]).
 static bool lu_solve6(double A[6][6], double b[6]) {
@@ -205,6 +248,19 @@ int gp_roi_crop(const uint8_t *images, int n_images, int H, int W, const int *im
     const dim3 grid((unsigned)((big * big / 4 + 255) / 256), (unsigned)B, roi_coord_2d ? 2u : 1u);
     roi_crop_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, H, W, image_index, masks, mask_index, inst_id, minv_img, minv_out, lut,
                                                             roi_img, roi_mask, roi_coord_2d, img_size, out_res);
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_resize_linear_u8_normalize(const uint8_t *images, int n_images, int H, int W, const int *image_index, const float *lut, float *out,
+                                  int B, int dh, int dw, void *stream) {
+    if (!images || !lut || !out) return GP_ERR_NULL;
+    if (B < 0 || B > 65535 || n_images <= 0 || H <= 0 || W <= 0 || dh <= 0 || dw <= 0) return GP_ERR_SHAPE;
+    if (H < dh || W < dw) return GP_ERR_UNSUPPORTED;   // upscaling: OpenCV takes another path (see the kernel comment)
+    if (B == 0) return GP_OK;
+    const double scale_x = 1.0 / ((double)dw / (double)W), scale_y = 1.0 / ((double)dh / (double)H);   // cv::resize: 1. / inv_scale
+    const dim3 grid((unsigned)((dh * dw + 255) / 256), (unsigned)B);
+    resize_linear_u8_norm_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(images, image_index, lut, out, H, W, dh, dw, scale_y, scale_x);
     count_launch();
     return (int)cudaGetLastError();
 }

@@ -131,19 +131,31 @@ def roi_crops(images: torch.Tensor, bbox_center, img_scale, image_index=0, masks
     return out
 
 
-def full_image_tensor(images: torch.Tensor, image_index=None, mean=IMG_MEAN, std=IMG_STD) -> torch.Tensor:
-    """``full_img`` of the loaders with ``FLAGS.resize_full`` off (``load_data_eval.py:345-347``, the input of ``Scale_net``):
-    ``(frame / 255.0 - mean) / std`` -> CHW float32, through the same double-precision table as the crops (bit-exact);
-    ``image_index`` (B,) repeats each frame for its RoIs like ``np.array([full_img] * len(roi_imgs))`` (``:348``)."""
-    if not images.is_cuda or images.dtype != torch.uint8 or images.shape[-1] != 3:
-        raise RuntimeError("full_image_tensor: images must be CUDA uint8 (M,H,W,3)")
+def full_image_tensor(images: torch.Tensor, image_index=None, resize=(256, 256), mean=IMG_MEAN, std=IMG_STD) -> torch.Tensor:
+    """``full_img`` of the loaders (the input of ``Scale_net``, ``load_data_eval.py:336-338,348``): ``cv2.resize(frame, resize)``
+    (INTER_LINEAR on uint8, ``FLAGS.resize_full`` -- the default) or the frame itself (``resize=None``), then
+    ``(v / 255.0 - mean) / std`` -> CHW float32; ``image_index`` (B,) repeats each frame for its RoIs like
+    ``np.array([full_img] * len(roi_imgs))``.  Bit-exact with the reference for frames at least as large as ``resize``
+    (``resize`` is (width, height) like cv2's dsize); smaller frames raise (OpenCV upscales on a different path)."""
+    if not images.is_cuda or images.dtype != torch.uint8 or images.shape[-1] != 3 or not images.is_contiguous():
+        raise RuntimeError("full_image_tensor: images must be contiguous CUDA uint8 (M,H,W,3)")
     if images.dim() == 3:
         images = images[None]
-    lut = normalisation_table(mean, std).to(images.device)
-    idx = images.long()
-    out = torch.stack([lut[c][idx[..., c]] for c in range(3)], dim=1)            # (M,3,H,W)
-    if image_index is not None:
-        out = out[torch.as_tensor(image_index, dtype=torch.long, device=images.device)]
+    M, H, W, _ = images.shape
+    dev = images.device
+    lut = normalisation_table(mean, std).to(dev)
+    if resize is None:
+        idx = images.long()
+        out = torch.stack([lut[c][idx[..., c]] for c in range(3)], dim=1)            # (M,3,H,W)
+        return out if image_index is None else out[torch.as_tensor(image_index, dtype=torch.long, device=dev)]
+    dw, dh = int(resize[0]), int(resize[1])
+    B = M if image_index is None else len(image_index)
+    iidx = None if image_index is None else _i32(image_index, B, dev, "image_index", 0, M)
+    out = torch.empty((B, 3, dh, dw), dtype=torch.float32, device=dev)
+    vp = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    with torch.cuda.device(dev):
+        check(lib.gp_resize_linear_u8_normalize(vp(images), M, H, W, vp(iidx), vp(lut), vp(out), B, dh, dw,
+                                                ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)), "resize_linear_u8_normalize")
     return out
 
 

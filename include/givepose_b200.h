@@ -202,6 +202,13 @@ int gp_roi_crop(const uint8_t *images, int n_images, int H, int W, const int *im
                 const int *mask_index, const int *inst_id, const double *minv_img, const double *minv_out, const float *lut,
                 float *roi_img, float *roi_mask, float *roi_coord_2d, int B, int img_size, int out_res, void *stream);
 
+/* full_img of the loaders with FLAGS.resize_full (the default): cv2.resize(frame, (dw, dh)) -- INTER_LINEAR, 8-bit fixed point --
+ * then (v/255 - mean)/std through the same table, HWC -> CHW (evaluation/load_data_eval.py:336-338).  images (n_images,H,W,3)
+ * uint8, image_index (B,) int32 or NULL (RoI b reads frame b), out (B,3,dh,dw) fp32.  Bit-exact against OpenCV 4.8 for
+ * H >= dh and W >= dw; upscaling is refused (GP_ERR_UNSUPPORTED). */
+int gp_resize_linear_u8_normalize(const uint8_t *images, int n_images, int H, int W, const int *image_index, const float *lut, float *out,
+                                  int B, int dh, int dw, void *stream);
+
 /* Dense layer on the tcgen05 tensor cores: y[M,N] = act(x[M,K] . w[N,K]^T + bias[N]), x / w / y bf16 row-major, bias fp32,
  * fp32 accumulation in TMEM, bias + activation in the epilogue (act: 0 none, 1 LeakyReLU(slope), 2 ReLU).  The shape of
  * every Linear / 1x1 convolution of the heads: DCNv3 input_proj / output_proj / offset / mask (modules/dcnv3.py:325-354),

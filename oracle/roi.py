@@ -136,3 +136,39 @@ def roi_tensors(image, mask, bbox_center, img_scale, inst_id=-1, img_size=256, o
     mt = mask.astype(np.float32) if inst_id < 0 else (mask == inst_id).astype(np.float32)
     roi_mask = crop_resize_nearest(mt, bbox_center, img_scale, img_size)[None]
     return roi_img, roi_mask, roi_coord.astype(np.float32)
+
+
+def resize_linear_u8(img, dw, dh):
+    """cv2.resize(img, (dw, dh)) for uint8 images, INTER_LINEAR: OpenCV's fixed-point path (resize.cpp: INTER_RESIZE_COEF_BITS = 11,
+    HResizeLinear + VResizeLinear<uchar>), exact for downscaling / same size (the loaders' 480x640 -> 256x256, load_data_eval.py:336)."""
+    def coeffs(n_dst, n_src):
+        scale = 1.0 / (np.float64(n_dst) / np.float64(n_src))
+        idx = np.zeros(n_dst, np.int64)
+        a = np.zeros((n_dst, 2), np.int64)
+        for d in range(n_dst):
+            f = np.float32((d + 0.5) * scale - 0.5)
+            s = int(np.floor(f))
+            f = np.float32(f - np.float32(s))
+            if s < 0:
+                f, s = np.float32(0), 0
+            if s >= n_src - 1:
+                f, s = np.float32(0), n_src - 1
+            idx[d] = s
+            a[d, 0] = int(np.rint(np.float32((np.float32(1.0) - f) * np.float32(2048))))
+            a[d, 1] = int(np.rint(np.float32(f * np.float32(2048))))
+        return idx, a
+    H, W = img.shape[:2]
+    xi, xa = coeffs(dw, W)
+    yi, ya = coeffs(dh, H)
+    src = img.astype(np.int64)
+    x1, y1 = np.minimum(xi + 1, W - 1), np.minimum(yi + 1, H - 1)
+    rows = src[:, xi, :] * xa[None, :, 0, None] + src[:, x1, :] * xa[None, :, 1, None]
+    b0, b1 = ya[:, 0][:, None, None], ya[:, 1][:, None, None]
+    out = (((b0 * (rows[yi] >> 4)) >> 16) + ((b1 * (rows[y1] >> 4)) >> 16) + 2) >> 2
+    return np.clip(out, 0, 255).astype(np.uint8)
+
+
+def full_img(image, resize=(256, 256), mean=(0.485, 0.456, 0.406), std=(0.229, 0.224, 0.225)):
+    """load_data_eval.py:336-338: optional cv2.resize, normalisation, HWC -> CHW (float32 at tensor creation, :364)."""
+    im = resize_linear_u8(image, *resize) if resize is not None else image
+    return ((im / 255.0 - mean) / std).transpose(2, 0, 1).astype(np.float32)

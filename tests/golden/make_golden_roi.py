@@ -35,5 +35,11 @@ for i, (cx, cy, s, S, R, iid) in enumerate(cases):
     out[f"c{i}/roi_coord_2d"] = roi_coord.astype(np.float32)
     out[f"c{i}/trans_img"] = get_affine_transform(c, (s, s), 0, (S, S))     # the tuple form crop_resize_by_warp_affine passes on
     out[f"c{i}/trans_out"] = get_affine_transform(c, (s, s), 0, (R, R))
+# full_img (load_data_eval.py:336-338 with FLAGS.resize_full, the default): cv2.resize -> normalise -> CHW
+frame = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+full = cv2.resize(frame, (64, 48))
+out["full/frame"] = frame
+out["full/resized_u8"] = full
+out["full/full_img"] = ((full / 255.0 - MEAN) / STD).transpose(2, 0, 1).astype(np.float32)
 np.savez_compressed(os.path.join(HERE, "roi.npz"), **out)
 print("wrote", os.path.join(HERE, "roi.npz"), os.path.getsize(os.path.join(HERE, "roi.npz")), "bytes")

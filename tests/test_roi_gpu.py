@@ -101,9 +101,27 @@ def test_detections_to_posenet_forward(roi):
     assert out["rot"].shape == (B, 3, 3) and torch.equal(out["rot"], ref["rot"]) and torch.equal(out["trans"], ref["trans"])
 
 
-def test_full_image_tensor_is_the_loaders_normalisation(roi):
+def test_full_image_tensor_matches_the_loaders(roi):
+    """load_data_eval.py:336-338,348: cv2.resize(frame, (256, 256)) -> normalise -> CHW, repeated per RoI; bit-exact against the
+    golden made by cv2, the oracle at the loaders' frame size, and live cv2; without resize it is the plain normalisation."""
+    frame = torch.from_numpy(G["full/frame"]).cuda()
+    got = roi.full_image_tensor(frame, resize=(64, 48))
+    assert got.shape == (1, 3, 48, 64) and np.array_equal(got[0].cpu().numpy(), G["full/full_img"])
     rng = np.random.default_rng(4)
-    frames = rng.integers(0, 256, (2, 48, 64, 3), dtype=np.uint8)
+    frames = rng.integers(0, 256, (2, 480, 640, 3), dtype=np.uint8)
     got = roi.full_image_tensor(torch.from_numpy(frames).cuda(), image_index=[1, 0, 1]).cpu().numpy()
-    want = np.stack([((f / 255.0 - roi.IMG_MEAN) / roi.IMG_STD).transpose(2, 0, 1).astype(np.float32) for f in frames])[[1, 0, 1]]
-    assert got.shape == (3, 3, 48, 64) and np.array_equal(got, want)   # load_data_eval.py:346-348
+    want = np.stack([O.full_img(f) for f in frames])[[1, 0, 1]]
+    assert got.shape == (3, 3, 256, 256) and np.array_equal(got, want)
+    try:
+        import cv2
+        for k, f in enumerate(frames):
+            ref = ((cv2.resize(f, (256, 256)) / 255.0 - roi.IMG_MEAN) / roi.IMG_STD).transpose(2, 0, 1).astype(np.float32)
+            assert np.array_equal(want[[1, 0, 1].index(k)], ref)
+    except ImportError:
+        pass
+    small = rng.integers(0, 256, (2, 48, 64, 3), dtype=np.uint8)
+    plain = roi.full_image_tensor(torch.from_numpy(small).cuda(), image_index=[1, 0, 1], resize=None).cpu().numpy()
+    want = np.stack([((f / 255.0 - roi.IMG_MEAN) / roi.IMG_STD).transpose(2, 0, 1).astype(np.float32) for f in small])[[1, 0, 1]]
+    assert np.array_equal(plain, want)
+    with pytest.raises(RuntimeError):
+        roi.full_image_tensor(torch.from_numpy(small).cuda())      # 48 x 64 -> 256 x 256 would be an upscale: refused

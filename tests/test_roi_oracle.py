@@ -71,3 +71,14 @@ def test_oracle_equals_live_cv2():
             assert np.array_equal(Mf, O.get_affine_transform_cv(*O.affine_points(ci, si, out)))
             want = cv2.warpAffine(src, Mf, (out, out), flags=cv2.INTER_NEAREST)
             assert np.array_equal(want, O.crop_resize_nearest(src, ci, si, out))
+
+
+def test_full_img_resize_oracle_equals_reference_golden_and_live_cv2():
+    """cv2.resize(frame, (w, h)) on uint8 (load_data_eval.py:336, FLAGS.resize_full default True) restated in fixed point."""
+    assert np.array_equal(O.resize_linear_u8(G["full/frame"], 64, 48), G["full/resized_u8"])
+    assert np.array_equal(O.full_img(G["full/frame"], (64, 48)), G["full/full_img"])
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(7)
+    for H, W in ((480, 640), (375, 500), (256, 256), (720, 1280), (300, 257)):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        assert np.array_equal(O.resize_linear_u8(img, 256, 256), cv2.resize(img, (256, 256))), (H, W)
