@@ -472,6 +472,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                     red_add_v4(reinterpret_cast<float *>(g3 + Cb * GS) + c4, mw[3] * go[c4], mw[3] * go[c4 + 1], mw[3] * go[c4 + 2], mw[3] * go[c4 + 3]);
                 }
                 unit_reduce3<L>(s_m, s_w_, s_h, cl);
+                __syncwarp();   // memory ordering: every lane of the unit has read record k before it is overwritten (shuffles only converge)
                 park(k, s_m, s_w_, s_h);
             }
         } else {
@@ -496,6 +497,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 }
                 // sum over the gc channels of the group = reduction over the L lanes of this unit (no block barriers)
                 unit_reduce3<L>(s_m, s_w_, s_h, cl);
+                __syncwarp();
                 if (valid) park(k, s_m, s_w_, s_h);
             }
         }
