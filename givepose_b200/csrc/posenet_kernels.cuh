@@ -802,16 +802,35 @@ upsample2x_strip_kernel(const T *__restrict__ x, T *__restrict__ y, int H, int W
     T *out = y + (long long)n * Ho * Wo * C + (long long)ow * C + V * cq;
     const int oh0 = blockIdx.y * rows_per_cta, oh1 = min(Ho, oh0 + rows_per_cta);
     const long long rs = (long long)W * C, ors = (long long)Wo * C;
-#pragma unroll 2
+    // the two source rows stay in registers while the output row walks down: the source row index advances every second
+    // output row (ry ~ 1/2), and then only ONE new row is loaded (the old lower row becomes the upper one)
+    float a[V], b[V], c[V], d[V];
+    int cy0 = -2, cy1 = -2;
     for (int oh = oh0; oh < oh1; ++oh) {
         const float fy = (float)oh * ry;
         const int y0 = min((int)fy, H - 1), y1 = min(y0 + 1, H - 1);
         const float ly = fy - (float)y0;
-        float a[V], b[V], c[V], d[V], o[V];
-        Vec<T, V>::load(c0 + y0 * rs, a);
-        Vec<T, V>::load(c1 + y0 * rs, b);
-        Vec<T, V>::load(c0 + y1 * rs, c);
-        Vec<T, V>::load(c1 + y1 * rs, d);
+        if (y0 != cy0) {
+            if (y0 == cy1) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) { a[k] = c[k]; b[k] = d[k]; }
+            } else {
+                Vec<T, V>::load(c0 + y0 * rs, a);
+                Vec<T, V>::load(c1 + y0 * rs, b);
+            }
+            cy0 = y0;
+        }
+        if (y1 != cy1) {
+            if (y1 == y0) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) { c[k] = a[k]; d[k] = b[k]; }
+            } else {
+                Vec<T, V>::load(c0 + y1 * rs, c);
+                Vec<T, V>::load(c1 + y1 * rs, d);
+            }
+            cy1 = y1;
+        }
+        float o[V];
         if (sizeof(T) == 4) {
 #pragma unroll
             for (int k = 0; k < V; ++k) {   // torch: h0 * (w0 * v00 + w1 * v01) + h1 * (w0 * v10 + w1 * v11)
