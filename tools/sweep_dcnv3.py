@@ -49,14 +49,17 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_dcnv3.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--shape", default="", help="only the shape with this name (K_N64 | M_64to32_N256)")
     a = ap.parse_args()
     shapes = [("K_N64", 64, 64, 64, 8, 32, 1, False), ("M_64to32_N256", 256, 64, 64, 4, 64, 2, True)]
     tiles = [(8, 8, 1), (8, 8, 2), (8, 8, 4), (4, 16, 1), (8, 16, 1), (4, 8, 1), (4, 4, 1), (4, 4, 2), (4, 4, 4), (4, 4, 8),
-             (2, 32, 1), (4, 8, 2), (4, 8, 4)]
+             (2, 32, 1), (4, 8, 2), (4, 8, 4), (16, 8, 1), (16, 4, 2), (16, 4, 1), (8, 4, 4), (16, 2, 4)]
     if a.quick:
         tiles = tiles[:3]
     rows = []
     for name, N, H, W, G, gc, s, full in shapes:
+        if a.shape and name != a.shape:
+            continue
         for dtype, dn in ((torch.float32, "f32"), (torch.bfloat16, "bf16")):
             for dist in ("T", "M"):
                 (inp, off, m, gout), Ho, Wo = inputs(N, H, W, G, gc, s, dist, dtype, full)
