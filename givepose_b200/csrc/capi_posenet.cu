@@ -287,6 +287,25 @@ int gp_upsample_bilinear2x_backward(const void *dy, void *dx, int N, int H, int 
     return (int)cudaGetLastError();
 }
 
+int gp_bias_add_relu(void *y, const void *residual, const float *bias, long long rows, int C, int dtype, void *stream) {
+    if (!y || !residual || !bias) return GP_ERR_NULL;
+    if (rows < 0 || C <= 0 || C % 8) return GP_ERR_SHAPE;
+    if (!al16(y) || !al16(residual)) return GP_ERR_ALIGN;
+    if (rows == 0) return GP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int V = dtype == GP_F32 ? 4 : 8;
+    const long long n_vec = rows * C / V, want = (n_vec + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148ll * 32 ? want : 148ll * 32);
+    switch (dtype) {
+        case GP_F32: bias_add_relu_kernel<float><<<grid, 256, 0, st>>>((float *)y, (const float *)residual, bias, n_vec, C); break;
+        case GP_BF16: bias_add_relu_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>((__nv_bfloat16 *)y, (const __nv_bfloat16 *)residual, bias, n_vec, C); break;
+        case GP_F16: bias_add_relu_kernel<__half><<<grid, 256, 0, st>>>((__half *)y, (const __half *)residual, bias, n_vec, C); break;
+        default: return GP_ERR_DTYPE;
+    }
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
 int gp_stem_s2d_pack(const float *img, void *out, int N, int H, int W, int dtype, void *stream) {
     if (!img || !out) return GP_ERR_NULL;
     if (N <= 0 || H <= 0 || W <= 0 || H % 2 || W % 2) return GP_ERR_SHAPE;

@@ -932,6 +932,25 @@ stem_s2d_pack_kernel(const float *__restrict__ img, T *__restrict__ out, int N, 
     }
 }
 
+// y = relu(y + bias[c] + residual), in place, channel-last (rows, C): the tail of a residual block when the convolution
+// runs without cuDNN's fused add+ReLU epilogue (whose kernels for 64 / 128 channels run at a third of the plain convolution's
+// rate on B200: 0.68 ms against 0.25 ms per 1024 RoIs at 64x64x64).  One pass, 16-byte vectors.
+template <typename T>
+__global__ void __launch_bounds__(256)
+bias_add_relu_kernel(T *__restrict__ y, const T *__restrict__ res, const float *__restrict__ bias, long long n_vec, int C) {
+    constexpr int V = 16 / (int)sizeof(T);
+    const int q = C / V;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n_vec; i += (long long)gridDim.x * blockDim.x) {
+        const int c0 = (int)(i % q) * V;
+        float a[V], r[V];
+        Vec<T, V>::load_stream(y + i * V, a);
+        Vec<T, V>::load_stream(res + i * V, r);
+#pragma unroll
+        for (int k = 0; k < V; ++k) a[k] = fmaxf(a[k] + __ldg(bias + c0 + k) + r[k], 0.f);
+        Vec<T, V>::store_stream(y + i * V, a);
+    }
+}
+
 // MaxPool2d(kernel 3, stride 2, pad 1) on channel-last activations (network/resnet.py:106 in the stand-in backbone).
 template <typename T>
 __global__ void __launch_bounds__(256)

@@ -284,6 +284,20 @@ class UpsampleBilinear2x(torch.autograd.Function):
         return upsample_bilinear2x_backward(dy.contiguous())
 
 
+def bias_add_relu_(y, residual, bias):
+    """In place ``y = relu(y + bias + residual)`` on channel-last ``y`` (..., C); ``bias`` fp32 (C,).  Returns ``y``."""
+    _need_cuda("y", y)
+    _need_cuda("residual", residual, y.dtype)
+    _need_cuda("bias", bias, torch.float32)
+    dt = _DTYPES.get(y.dtype)
+    C = y.shape[-1]
+    if dt is None or residual.shape != y.shape or bias.numel() != C:
+        raise RuntimeError("bias_add_relu_: inconsistent shapes / dtype")
+    with torch.cuda.device(y.device):
+        check(lib.gp_bias_add_relu(_vp(y), _vp(residual), _vp(bias), y.numel() // C, C, dt, _stream(y)), "bias_add_relu")
+    return y
+
+
 def maxpool3x3s2(x, relu=False):
     """``MaxPool2d(3, 2, 1)`` on channel-last ``x`` (N,H,W,C); ``relu=True`` computes ``maxpool(relu(x))`` in the same pass."""
     dt = _nhwc("input", x)

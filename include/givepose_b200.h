@@ -237,6 +237,9 @@ int gp_upsample_bilinear2x_backward(const void *dy, void *dx, int N, int H, int 
 
 /* MaxPool2d(3, stride 2, pad 1) on channel-last activations (stem of the stand-in ResNet backbone, resnet.py:106):
  * (N,H,W,C) -> (N,(H-1)/2+1,(W-1)/2+1,C).  relu != 0 computes maxpool(relu(x)) (= relu(maxpool(x))) in the same pass. */
+/* y = relu(y + bias[c] + residual) in place on channel-last (rows, C) activations: tail of a residual block of the stand-in
+ * backbone when the convolution runs without cuDNN's fused add+ReLU epilogue.  bias fp32 [C]; C % 8 == 0. */
+int gp_bias_add_relu(void *y, const void *residual, const float *bias, long long rows, int C, int dtype, void *stream);
 int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream);
 
 /* rot6 (B,6) + t (B,3: centroid dx, dy, relative z) -> ego rotation (B,3,3) and translation (B,3):
