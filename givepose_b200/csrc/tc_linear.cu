@@ -309,6 +309,208 @@ static bool make_map(CUtensorMap *map, const void *ptr, int rows, int K, int box
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// Stem of the stand-in backbone as an implicit GEMM on the tensor cores: the 7x7/2 convolution runs as a 4x4/1 convolution
+// over the packed 2x2 space-to-depth image P (N, Hp, Wp, 16) (stem_s2d_pack), i.e. out[(n,y,x), o] = sum_{dy<4} sum_{j<64}
+// P[n, y+dy, x .. x+3, :][j] * W[o, dy*64 + j]: four K = 64 blocks, each a row of 64 CONTIGUOUS elements of P.  A tensor map with
+// overlapping rows (row pitch 16 elements = 32 bytes, row length 64) makes TMA do the im2col: the block of output row y and tap dy
+// is the box {64, 128} at flat pixel (n*Hp + y+dy)*Wp -- and it is the SAME block output row y+1 needs for tap dy-1, so a CTA
+// walking down an image loads ONE new 16 KB block per 128-pixel output row and keeps the last four in a ring (cuDNN's kernel
+// for this layer runs at 0.2 PFLOP/s: 2.8 ms per 1024 RoIs).  The weights (64 x 256 bf16 = 32 KB) stay in shared memory for the
+// whole kernel.  Roles as in linear_bf16_kernel: TMA producer warp, MMA warp (tcgen05.mma M128 N64 K16, fp32 accumulators double
+// buffered in TMEM), four epilogue warps (bias + ReLU, bf16, row-contiguous stores).
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace stem {
+constexpr int BN = 64, RING = 8, ROWS_PER_ITEM = 32, TAPS = 4;
+constexpr int BLK_BYTES = BM * BK * 2;              // one im2col block: 128 pixels x 64 elements
+constexpr int W_BYTES = TAPS * BN * BK * 2;         // resident weights: 4 K-blocks of 64 rows x 128 bytes
+constexpr int OUT_BYTES = BM * BN * 2;
+constexpr int TMEM_COLS = 2 * BN;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)RING * BLK_BYTES + W_BYTES + OUT_BYTES + 4 * BN * 4 + 256;
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}   // namespace stem
+
+__global__ void __launch_bounds__(THREADS, 1)
+stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w, const float *__restrict__ bias,
+                     __nv_bfloat16 *__restrict__ y, int n_img, int Hp, int Wp, int Ho) {
+    using namespace stem;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t w_base = base + RING * BLK_BYTES;
+    const uint32_t out_stage = w_base + W_BYTES;
+    const uint32_t bias_stage = out_stage + OUT_BYTES;
+    const uint32_t bars = bias_stage + 4 * BN * 4;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (RING + s); };
+    auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * RING + a); };
+    auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * RING + 2 + a); };
+    const uint32_t w_bar = bars + 8u * (2 * RING + 4);
+    const uint32_t tmem_slot = bars + 8u * (2 * RING + 5);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int chunks = (Ho + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM;        // work item = (image, chunk of ROWS_PER_ITEM output rows)
+    const int items = n_img * chunks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < RING; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full_bar(a), 1);
+            mbar_init(tmem_empty_bar(a), 4);
+        }
+        mbar_init(w_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===== TMA producer: the weights once, then one im2col block per input row of every work item =====
+        if (lane == 0) {
+            mbar_expect_tx(w_bar, W_BYTES);
+            for (int kb = 0; kb < TAPS; ++kb) tma_load_2d(w_base + kb * (BN * BK * 2), &map_w, w_bar, kb * BK, 0);
+            uint32_t g = 0;   // blocks issued so far
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
+                const int rows = min(ROWS_PER_ITEM, Ho - y0);
+                for (int r = 0; r < rows + TAPS - 1; ++r, ++g) {
+                    const int s = g % RING;
+                    const uint32_t ph = (g / RING) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), BLK_BYTES);
+                    tma_load_2d(base + s * BLK_BYTES, &map_v, full_bar(s), 0, (n * Hp + y0 + r) * Wp);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            mbar_wait(w_bar, 0u);
+            uint32_t g0 = 0, waited = 0, lt = 0;   // first block of the item / blocks whose arrival has been observed / tiles done
+            for (int item = blockIdx.x; item < items; item += gridDim.x) {
+                const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
+                const int rows = min(ROWS_PER_ITEM, Ho - y0);
+                (void)n;
+                for (int t = 0; t < rows; ++t, ++lt) {
+                    const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+                    mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
+                    while (waited <= g0 + t + TAPS - 1) {   // blocks arrive in issue order; each is waited for exactly once
+                        mbar_wait(full_bar(waited % RING), (waited / RING) & 1u);
+                        ++waited;
+                    }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t tmem_d = tmem_base + acc * BN;
+#pragma unroll
+                    for (int dy = 0; dy < TAPS; ++dy) {
+                        const uint32_t a_addr = base + ((g0 + t + dy) % RING) * BLK_BYTES, b_addr = w_base + dy * (BN * BK * 2);
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma_bf16(tmem_d, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), IDESC, (dy | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar((g0 + t) % RING));          // input row y0+t is not needed by the rows below
+                    if (t == rows - 1)
+                        for (int e = 1; e < TAPS; ++e) umma_commit(empty_bar((g0 + t + e) % RING));
+                    umma_commit(tmem_full_bar(acc));
+                }
+                g0 += rows + TAPS - 1;
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 2..5 =====
+        const int q = warp & 3;
+        constexpr int ROW_BYTES = BN * 2, CHUNKS = BN / 8;
+        uint8_t *stage = smem_gen + (out_stage - base) + q * (32 * ROW_BYTES);
+        float *s_bias = reinterpret_cast<float *>(smem_gen + (bias_stage - base)) + q * BN;
+#pragma unroll
+        for (int j = lane; j < BN; j += 32) s_bias[j] = __ldg(bias + j);
+        __syncwarp();
+        uint32_t lt = 0;
+        for (int item = blockIdx.x; item < items; item += gridDim.x) {
+            const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
+            const int rows = min(ROWS_PER_ITEM, Ho - y0);
+            for (int t = 0; t < rows; ++t, ++lt) {
+                const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+                mbar_wait(tmem_full_bar(acc), acc_ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+                for (int c = 0; c < BN; c += 32) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + (uint32_t)c;
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const float a = fmaxf(__uint_as_float(r[j + 2 * u]) + s_bias[c + j + 2 * u], 0.f);
+                            const float b = fmaxf(__uint_as_float(r[j + 2 * u + 1]) + s_bias[c + j + 2 * u + 1], 0.f);
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                            pk[u] = *reinterpret_cast<const uint32_t *>(&h);
+                        }
+                        const int chunk = (c + j) >> 3;
+                        *reinterpret_cast<uint4 *>(stage + lane * ROW_BYTES + ((chunk ^ (lane & (CHUNKS - 1))) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                    }
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
+                // output row (n, y0 + t): 128 pixels x 64 channels contiguous; this warp writes pixels 32q .. 32q+31
+                __nv_bfloat16 *dst = y + (((size_t)n * Ho + (y0 + t)) * BM + q * 32) * BN;
+                constexpr int ROWS_PER_IT = 32 / CHUNKS;   // 4 pixels per warp-wide 16-byte store
+                const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+#pragma unroll
+                for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+                    const int rl = ROWS_PER_IT * it + rsub;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + rl * ROW_BYTES + ((chunk ^ (rl & (CHUNKS - 1))) << 4));
+                    *reinterpret_cast<uint4 *>(dst + (size_t)rl * BN + chunk * 8) = v;
+                }
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)stem::TMEM_COLS) : "memory");
+    }
+}
+
+// overlapping-row view of the packed image: row r = 64 elements starting at flat pixel r (pitch 16 elements = 32 bytes)
+static bool make_im2col_map(CUtensorMap *map, const void *ptr, long long n_pixels) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)BK, (cuuint64_t)(n_pixels - 3)};
+    const cuuint64_t strides[1] = {(cuuint64_t)16 * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 }  // namespace tc
 }  // namespace gp
 
@@ -357,3 +559,30 @@ extern "C" int gp_linear_bf16(const void *x, const void *w, const float *bias, v
     if (N > 128 && tiles256 >= 148) return launch_linear_act<256>(x, w, bias, y, M, N, K, act, slope, (cudaStream_t)stream);
     return launch_linear_act<128>(x, w, bias, y, M, N, K, act, slope, (cudaStream_t)stream);
 }
+
+extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, void *stream) {
+    using namespace gp::tc;
+    if (!packed || !w || !bias || !y) return GP_ERR_NULL;
+    const int Ho = Hp - 3, Wo = Wp - 3;
+    if (N <= 0 || Ho <= 0 || Wo != BM) return GP_ERR_UNSUPPORTED;   // one 128-pixel output row per tile (256 x 256 crops)
+    if ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
+    if ((long long)N * Hp * Wp >= (1ll << 31)) return GP_ERR_SHAPE;
+    static bool attr_set = false;
+    static int sms = 0;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(stem_s2d_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        attr_set = true;
+    }
+    CUtensorMap mv, mw;
+    if (!make_im2col_map(&mv, packed, (long long)N * Hp * Wp) || !make_map(&mw, w, stem::BN, stem::TAPS * BK, stem::BN)) return GP_ERR_UNSUPPORTED;
+    const int items = N * ((Ho + stem::ROWS_PER_ITEM - 1) / stem::ROWS_PER_ITEM);
+    const unsigned grid = (unsigned)(items < sms ? items : sms);
+    stem_s2d_gemm_kernel<<<grid, THREADS, stem::SMEM_BYTES, (cudaStream_t)stream>>>(mv, mw, bias, (__nv_bfloat16 *)y, N, Hp, Wp, Ho);
+    gp::g_launches += 1;
+    return (int)cudaGetLastError();
+}
+

@@ -249,6 +249,22 @@ def stem_s2d_pack(img, dtype):
     return out
 
 
+def stem_s2d_gemm(packed, w2d, bias):
+    """relu(conv4x4/1(packed) + bias) on the tcgen05 tensor cores (``gp_stem_s2d_gemm``): ``packed`` (N,Hp,Wp,16) bf16 from
+    ``stem_s2d_pack``, ``w2d`` (64, 256) bf16 tap-major, ``bias`` fp32 (64,) -> (N,Hp-3,Wp-3,64) bf16.  Raises for unsupported
+    shapes (the caller falls back to cuDNN)."""
+    _need_cuda("packed", packed, torch.bfloat16)
+    _need_cuda("weight", w2d, torch.bfloat16)
+    _need_cuda("bias", bias, torch.float32)
+    N, Hp, Wp, C = packed.shape
+    if C != 16 or tuple(w2d.shape) != (64, 256) or bias.numel() != 64:
+        raise RuntimeError("stem_s2d_gemm: unsupported shapes")
+    y = torch.empty((N, Hp - 3, Wp - 3, 64), dtype=torch.bfloat16, device=packed.device)
+    with torch.cuda.device(packed.device):
+        check(lib.gp_stem_s2d_gemm(_vp(packed), _vp(w2d), _vp(bias), _vp(y), N, Hp, Wp, _stream(packed)), "stem_s2d_gemm")
+    return y
+
+
 def upsample_bilinear2x(x):
     """``nn.UpsamplingBilinear2d(scale_factor=2)`` (align_corners=True) on channel-last ``x``."""
     dt = _nhwc("input", x)

@@ -240,6 +240,11 @@ int gp_upsample_bilinear2x_backward(const void *dy, void *dx, int N, int H, int 
 /* y = relu(y + bias[c] + residual) in place on channel-last (rows, C) activations: tail of a residual block of the stand-in
  * backbone when the convolution runs without cuDNN's fused add+ReLU epilogue.  bias fp32 [C]; C % 8 == 0. */
 int gp_bias_add_relu(void *y, const void *residual, const float *bias, long long rows, int C, int dtype, void *stream);
+/* Stem of the stand-in backbone on the tcgen05 tensor cores: y (N, Hp-3, Wp-3, 64) = relu(conv4x4/1(packed) + bias), packed =
+ * gp_stem_s2d_pack's (N, Hp, Wp, 16) bf16 image, w [64][4*4*16] bf16 (tap-major: (dy, dx, c)), bias fp32 [64].  TMA does the
+ * im2col through a tensor map with overlapping rows; one new 16 KB block per output row, weights resident in shared memory.
+ * Supported: Wp - 3 == 128 (256 x 256 crops), bf16; anything else returns GP_ERR_UNSUPPORTED (callers fall back to cuDNN). */
+int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, void *stream);
 int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream);
 
 /* rot6 (B,6) + t (B,3: centroid dx, dy, relative z) -> ego rotation (B,3,3) and translation (B,3):

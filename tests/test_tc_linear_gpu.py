@@ -48,3 +48,23 @@ def test_linear_bf16_refuses_cpu_and_bad_k():
         ops.linear_bf16(torch.zeros(4, 64, dtype=torch.bfloat16), torch.zeros(8, 64, dtype=torch.bfloat16))
     with pytest.raises(RuntimeError, match="unsupported shapes"):
         ops.linear_bf16(torch.zeros(4, 60, dtype=torch.bfloat16).cuda(), torch.zeros(8, 60, dtype=torch.bfloat16).cuda())
+
+
+@pytest.mark.parametrize("N", [1, 3, 40])
+def test_stem_implicit_gemm_matches_cudnn(N):
+    """gp_stem_s2d_gemm (tcgen05 implicit GEMM, TMA im2col through an overlapping-row tensor map, ring of four input rows) against
+    the same 4x4 convolution through cuDNN on the same packed operand: bf16 outputs, fp32 accumulation on both sides."""
+    import torch.nn.functional as F
+    from givepose_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    img = torch.randn(N, 3, 256, 256, generator=g).cuda()
+    packed = ops.stem_s2d_pack(img, torch.bfloat16)                                  # (N, 131, 131, 16)
+    w = (torch.randn(64, 16, 4, 4, generator=g) * 0.1).bfloat16().cuda().contiguous(memory_format=torch.channels_last)
+    b = torch.randn(64, generator=g).cuda()
+    got = ops.stem_s2d_gemm(packed, w.permute(0, 2, 3, 1).reshape(64, 256), b)
+    want = F.relu(F.conv2d(packed.permute(0, 3, 1, 2).float(), w.float(), b)).permute(0, 2, 3, 1)
+    assert got.shape == (N, 128, 128, 64) and got.dtype == torch.bfloat16
+    err = ((got.float() - want).abs().max() / want.abs().max()).item()
+    assert err < 1e-2, err
+    # every output row / image is written exactly once: no stale memory
+    assert torch.isfinite(got.float()).all()
