@@ -55,7 +55,7 @@ EXPORTS = {
     "gp_upsample_bilinear2x": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "gp_upsample_bilinear2x_backward": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "gp_bias_add_relu": (_I, [_VP, _VP, _VP, ctypes.c_longlong, _I, _I, _VP]),
-    "gp_stem_s2d_gemm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
+    "gp_stem_s2d_gemm": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _VP]),
     "gp_maxpool3x3s2": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _I, _VP]),
     "gp_pose_decode": (_I, [_VP, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _I, _I, ctypes.c_float, _VP]),
     "gp_roi_affine_inverse": (_I, [_VP, _VP, _I, _I, _VP]),

@@ -325,12 +325,14 @@ namespace stem {
 constexpr int BN = 64, RING = 8, ROWS_PER_ITEM = 32, TAPS = 4;
 constexpr int BLK_BYTES = BM * BK * 2;              // one im2col block: 128 pixels x 64 elements
 constexpr int W_BYTES = TAPS * BN * BK * 2;         // resident weights: 4 K-blocks of 64 rows x 128 bytes
-constexpr int OUT_BYTES = BM * BN * 2;
+constexpr int OUT_BYTES = BM * BN * 2;              // one activated output row: 128 pixels x 64 channels bf16
+constexpr int OUT_ROWS = 3;                         // POOL: ring of the last three activated rows (3x3/2 max-pool window)
 constexpr int TMEM_COLS = 2 * BN;
-constexpr size_t SMEM_BYTES = 1024 + (size_t)RING * BLK_BYTES + W_BYTES + OUT_BYTES + 4 * BN * 4 + 256;
+constexpr size_t SMEM_BYTES = 1024 + (size_t)RING * BLK_BYTES + W_BYTES + OUT_ROWS * OUT_BYTES + 4 * BN * 4 + 256;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }   // namespace stem
 
+template <bool POOL>
 __global__ void __launch_bounds__(THREADS, 1)
 stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w, const float *__restrict__ bias,
                      __nv_bfloat16 *__restrict__ y, int n_img, int Hp, int Wp, int Ho) {
@@ -339,13 +341,22 @@ stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t w_base = base + RING * BLK_BYTES;
     const uint32_t out_stage = w_base + W_BYTES;
-    const uint32_t bias_stage = out_stage + OUT_BYTES;
+    const uint32_t bias_stage = out_stage + OUT_ROWS * OUT_BYTES;
     const uint32_t bars = bias_stage + 4 * BN * 4;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (RING + s); };
     auto tmem_full_bar = [&](int a) { return bars + 8u * (2 * RING + a); };
     auto tmem_empty_bar = [&](int a) { return bars + 8u * (2 * RING + 2 + a); };
     const uint32_t w_bar = bars + 8u * (2 * RING + 4);
+    // work item = (image, chunk of ROWS_PER_ITEM output rows); with POOL the chunk also computes the row above it (the pooling
+    // window of its first pooled row reaches one row up)
+    auto item_rows = [&](int item, int &n, int &ys, int &rows) {
+        const int chunks_ = (Ho + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM;
+        n = item / chunks_;
+        const int y0 = (item - n * chunks_) * ROWS_PER_ITEM;
+        ys = POOL && y0 > 0 ? y0 - 1 : y0;
+        rows = min(y0 + ROWS_PER_ITEM, Ho) - ys;
+    };
     const uint32_t tmem_slot = bars + 8u * (2 * RING + 5);
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
@@ -383,8 +394,8 @@ stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
             for (int kb = 0; kb < TAPS; ++kb) tma_load_2d(w_base + kb * (BN * BK * 2), &map_w, w_bar, kb * BK, 0);
             uint32_t g = 0;   // blocks issued so far
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
-                const int rows = min(ROWS_PER_ITEM, Ho - y0);
+                int n, y0, rows;
+                item_rows(item, n, y0, rows);
                 for (int r = 0; r < rows + TAPS - 1; ++r, ++g) {
                     const int s = g % RING;
                     const uint32_t ph = (g / RING) & 1u;
@@ -401,9 +412,9 @@ stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
             mbar_wait(w_bar, 0u);
             uint32_t g0 = 0, waited = 0, lt = 0;   // first block of the item / blocks whose arrival has been observed / tiles done
             for (int item = blockIdx.x; item < items; item += gridDim.x) {
-                const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
-                const int rows = min(ROWS_PER_ITEM, Ho - y0);
-                (void)n;
+                int n, y0, rows;
+                item_rows(item, n, y0, rows);
+                (void)n; (void)y0;
                 for (int t = 0; t < rows; ++t, ++lt) {
                     const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
                     mbar_wait(tmem_empty_bar(acc), acc_ph ^ 1u);
@@ -431,19 +442,27 @@ stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
         __syncwarp();
     } else {
         // ===== epilogue: warps 2..5 =====
-        const int q = warp & 3;
+        // TMEM -> bias + ReLU -> bf16 -> the activated row in shared memory (pixel-major, 16-byte chunks XOR-swizzled by the pixel).
+        // !POOL: the warp stores its 32 pixels.  POOL: the row goes into a ring of three; after every odd row y = 2 py + 1 the
+        // four warps together write pooled row py = max over rows 2py-1 .. 2py+1 x columns 2px-1 .. 2px+1 (MaxPool2d(3, 2, 1);
+        // ReLU commutes with max), so the pre-pool tensor never leaves the SM.
+        const int q = warp & 3, et = threadIdx.x - 64;   // 0..127 among the epilogue threads
         constexpr int ROW_BYTES = BN * 2, CHUNKS = BN / 8;
-        uint8_t *stage = smem_gen + (out_stage - base) + q * (32 * ROW_BYTES);
+        uint8_t *ring = smem_gen + (out_stage - base);
         float *s_bias = reinterpret_cast<float *>(smem_gen + (bias_stage - base)) + q * BN;
 #pragma unroll
         for (int j = lane; j < BN; j += 32) s_bias[j] = __ldg(bias + j);
         __syncwarp();
+        const int Hq = (Ho - 1) / 2 + 1, Wq = (BM - 1) / 2 + 1;   // pooled size
         uint32_t lt = 0;
         for (int item = blockIdx.x; item < items; item += gridDim.x) {
-            const int n = item / chunks, y0 = (item - n * chunks) * ROWS_PER_ITEM;
-            const int rows = min(ROWS_PER_ITEM, Ho - y0);
+            int n, ys, rows;
+            item_rows(item, n, ys, rows);
+            const int chunks_ = (Ho + ROWS_PER_ITEM - 1) / ROWS_PER_ITEM, y0 = (item - n * chunks_) * ROWS_PER_ITEM;
             for (int t = 0; t < rows; ++t, ++lt) {
+                const int yrow = ys + t;
                 const uint32_t acc = lt & 1u, acc_ph = (lt >> 1) & 1u;
+                uint8_t *stage = ring + (POOL ? (yrow % OUT_ROWS) * OUT_BYTES : 0) + q * (32 * ROW_BYTES);
                 mbar_wait(tmem_full_bar(acc), acc_ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
@@ -477,17 +496,53 @@ stem_s2d_gemm_kernel(const __grid_constant__ CUtensorMap map_v, const __grid_con
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty_bar(acc));
-                // output row (n, y0 + t): 128 pixels x 64 channels contiguous; this warp writes pixels 32q .. 32q+31
-                __nv_bfloat16 *dst = y + (((size_t)n * Ho + (y0 + t)) * BM + q * 32) * BN;
-                constexpr int ROWS_PER_IT = 32 / CHUNKS;   // 4 pixels per warp-wide 16-byte store
-                const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
+                if (!POOL) {
+                    // output row (n, yrow): 128 pixels x 64 channels contiguous; this warp writes pixels 32q .. 32q+31
+                    __nv_bfloat16 *dst = y + (((size_t)n * Ho + yrow) * BM + q * 32) * BN;
+                    constexpr int ROWS_PER_IT = 32 / CHUNKS;   // 4 pixels per warp-wide 16-byte store
+                    const int chunk = lane % CHUNKS, rsub = lane / CHUNKS;
 #pragma unroll
-                for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
-                    const int rl = ROWS_PER_IT * it + rsub;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(stage + rl * ROW_BYTES + ((chunk ^ (rl & (CHUNKS - 1))) << 4));
-                    *reinterpret_cast<uint4 *>(dst + (size_t)rl * BN + chunk * 8) = v;
+                    for (int it = 0; it < 32 / ROWS_PER_IT; ++it) {
+                        const int rl = ROWS_PER_IT * it + rsub;
+                        const uint4 v = *reinterpret_cast<const uint4 *>(stage + rl * ROW_BYTES + ((chunk ^ (rl & (CHUNKS - 1))) << 4));
+                        *reinterpret_cast<uint4 *>(dst + (size_t)rl * BN + chunk * 8) = v;
+                    }
+                    __syncwarp();
+                } else {
+                    asm volatile("bar.sync 1, 128;" ::: "memory");   // row yrow staged by all four warps
+                    const bool last = yrow == Ho - 1;
+                    if (((yrow & 1) || last) && yrow >= y0) {
+                        // pooled row py: odd yrow = 2py+1 closes its window; an even last row closes py = yrow/2 on its own
+                        const int py = yrow >> 1;
+                        if ((yrow & 1) ? (2 * py >= y0) : true) {
+                            // branch-free 3x3 window: taps outside the map are replaced by the nearest tap inside (max is idempotent),
+                            // so the nine 16-byte loads are unconditional and in flight together
+                            const uint8_t *rw[3] = {ring + (max(2 * py - 1, 0) % OUT_ROWS) * OUT_BYTES, ring + ((2 * py) % OUT_ROWS) * OUT_BYTES,
+                                                    ring + (min(2 * py + 1, Ho - 1) % OUT_ROWS) * OUT_BYTES};
+                            __nv_bfloat16 *dst = y + ((size_t)n * Hq + py) * Wq * BN;
+#pragma unroll 2
+                            for (int id = et; id < Wq * CHUNKS; id += 128) {
+                                const int px = id / CHUNKS, chunk = id - px * CHUNKS;
+                                const int cc[3] = {max(2 * px - 1, 0), 2 * px, min(2 * px + 1, BM - 1)};
+                                uint4 v[9];
+#pragma unroll
+                                for (int a = 0; a < 3; ++a)
+#pragma unroll
+                                    for (int b = 0; b < 3; ++b)
+                                        v[a * 3 + b] = *reinterpret_cast<const uint4 *>(rw[a] + cc[b] * ROW_BYTES + ((chunk ^ (cc[b] & (CHUNKS - 1))) << 4));
+                                __align__(16) __nv_bfloat162 m[4];
+#pragma unroll
+                                for (int u = 0; u < 4; ++u) {
+                                    m[u] = reinterpret_cast<const __nv_bfloat162 *>(&v[0])[u];
+#pragma unroll
+                                    for (int k = 1; k < 9; ++k) m[u] = __hmax2(m[u], reinterpret_cast<const __nv_bfloat162 *>(&v[k])[u]);
+                                }
+                                *reinterpret_cast<uint4 *>(dst + (size_t)px * BN + chunk * 8) = *reinterpret_cast<const uint4 *>(m);
+                            }
+                        }
+                        asm volatile("bar.sync 1, 128;" ::: "memory");   // the oldest ring slot is overwritten by the next row
+                    }
                 }
-                __syncwarp();
             }
         }
     }
@@ -560,7 +615,7 @@ extern "C" int gp_linear_bf16(const void *x, const void *w, const float *bias, v
     return launch_linear_act<128>(x, w, bias, y, M, N, K, act, slope, (cudaStream_t)stream);
 }
 
-extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, void *stream) {
+extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, int pool, void *stream) {
     using namespace gp::tc;
     if (!packed || !w || !bias || !y) return GP_ERR_NULL;
     const int Ho = Hp - 3, Wo = Wp - 3;
@@ -570,7 +625,8 @@ extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *
     static bool attr_set = false;
     static int sms = 0;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(stem_s2d_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(stem_s2d_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_s2d_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         int dev = 0;
         cudaGetDevice(&dev);
@@ -581,7 +637,8 @@ extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *
     if (!make_im2col_map(&mv, packed, (long long)N * Hp * Wp) || !make_map(&mw, w, stem::BN, stem::TAPS * BK, stem::BN)) return GP_ERR_UNSUPPORTED;
     const int items = N * ((Ho + stem::ROWS_PER_ITEM - 1) / stem::ROWS_PER_ITEM);
     const unsigned grid = (unsigned)(items < sms ? items : sms);
-    stem_s2d_gemm_kernel<<<grid, THREADS, stem::SMEM_BYTES, (cudaStream_t)stream>>>(mv, mw, bias, (__nv_bfloat16 *)y, N, Hp, Wp, Ho);
+    if (pool) stem_s2d_gemm_kernel<true><<<grid, THREADS, stem::SMEM_BYTES, (cudaStream_t)stream>>>(mv, mw, bias, (__nv_bfloat16 *)y, N, Hp, Wp, Ho);
+    else stem_s2d_gemm_kernel<false><<<grid, THREADS, stem::SMEM_BYTES, (cudaStream_t)stream>>>(mv, mw, bias, (__nv_bfloat16 *)y, N, Hp, Wp, Ho);
     gp::g_launches += 1;
     return (int)cudaGetLastError();
 }

@@ -249,9 +249,10 @@ def stem_s2d_pack(img, dtype):
     return out
 
 
-def stem_s2d_gemm(packed, w2d, bias):
+def stem_s2d_gemm(packed, w2d, bias, pool=False):
     """relu(conv4x4/1(packed) + bias) on the tcgen05 tensor cores (``gp_stem_s2d_gemm``): ``packed`` (N,Hp,Wp,16) bf16 from
-    ``stem_s2d_pack``, ``w2d`` (64, 256) bf16 tap-major, ``bias`` fp32 (64,) -> (N,Hp-3,Wp-3,64) bf16.  Raises for unsupported
+    ``stem_s2d_pack``, ``w2d`` (64, 256) bf16 tap-major, ``bias`` fp32 (64,) -> (N,Hp-3,Wp-3,64) bf16; ``pool=True`` applies
+    the backbone's ``MaxPool2d(3, 2, 1)`` in the epilogue and returns the pooled (N,64,64,64) tensor.  Raises for unsupported
     shapes (the caller falls back to cuDNN)."""
     _need_cuda("packed", packed, torch.bfloat16)
     _need_cuda("weight", w2d, torch.bfloat16)
@@ -259,9 +260,11 @@ def stem_s2d_gemm(packed, w2d, bias):
     N, Hp, Wp, C = packed.shape
     if C != 16 or tuple(w2d.shape) != (64, 256) or bias.numel() != 64:
         raise RuntimeError("stem_s2d_gemm: unsupported shapes")
-    y = torch.empty((N, Hp - 3, Wp - 3, 64), dtype=torch.bfloat16, device=packed.device)
+    Ho, Wo = Hp - 3, Wp - 3
+    shape = (N, (Ho - 1) // 2 + 1, (Wo - 1) // 2 + 1, 64) if pool else (N, Ho, Wo, 64)
+    y = torch.empty(shape, dtype=torch.bfloat16, device=packed.device)
     with torch.cuda.device(packed.device):
-        check(lib.gp_stem_s2d_gemm(_vp(packed), _vp(w2d), _vp(bias), _vp(y), N, Hp, Wp, _stream(packed)), "stem_s2d_gemm")
+        check(lib.gp_stem_s2d_gemm(_vp(packed), _vp(w2d), _vp(bias), _vp(y), N, Hp, Wp, int(bool(pool)), _stream(packed)), "stem_s2d_gemm")
     return y
 
 

@@ -667,8 +667,8 @@ def _stem_s2d(img, conv, bn, dtype):
     if dtype == torch.bfloat16 and packed.shape[2] - 3 == 128 and w.shape[0] == 64 and _stem_s2d.tc_ok:
         # hand-written tcgen05 implicit GEMM (TMA im2col through an overlapping-row tensor map): 2.8 -> 0.8 ms per 1024 RoIs
         try:
-            y = ops.stem_s2d_gemm(packed, w.permute(0, 2, 3, 1).reshape(64, 256), _cached(b, torch.float32, tag="f32bias"))
-            return ops.maxpool3x3s2(y, relu=True).permute(0, 3, 1, 2)
+            y = ops.stem_s2d_gemm(packed, w.permute(0, 2, 3, 1).reshape(64, 256), _cached(b, torch.float32, tag="f32bias"), pool=True)
+            return y.permute(0, 3, 1, 2)   # bias + ReLU + the 3x3/2 max-pool happened in the kernel's epilogue
         except RuntimeError:
             _stem_s2d.tc_ok = False   # e.g. the driver refuses the tensor map: cuDNN path below
     x = packed.permute(0, 3, 1, 2)

@@ -243,8 +243,10 @@ int gp_bias_add_relu(void *y, const void *residual, const float *bias, long long
 /* Stem of the stand-in backbone on the tcgen05 tensor cores: y (N, Hp-3, Wp-3, 64) = relu(conv4x4/1(packed) + bias), packed =
  * gp_stem_s2d_pack's (N, Hp, Wp, 16) bf16 image, w [64][4*4*16] bf16 (tap-major: (dy, dx, c)), bias fp32 [64].  TMA does the
  * im2col through a tensor map with overlapping rows; one new 16 KB block per output row, weights resident in shared memory.
+ * pool != 0: the 3x3/2 max-pool (pad 1) that follows in the backbone is applied in the epilogue (a ring of the last three
+ * activated rows in shared memory) and y is the pooled (N, 64, 64, 64) tensor: the pre-pool activation never leaves the SM.
  * Supported: Wp - 3 == 128 (256 x 256 crops), bf16; anything else returns GP_ERR_UNSUPPORTED (callers fall back to cuDNN). */
-int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, void *stream);
+int gp_stem_s2d_gemm(const void *packed, const void *w, const float *bias, void *y, int N, int Hp, int Wp, int pool, void *stream);
 int gp_maxpool3x3s2(const void *x, void *y, int N, int H, int W, int C, int relu, int dtype, void *stream);
 
 /* rot6 (B,6) + t (B,3: centroid dx, dy, relative z) -> ego rotation (B,3,3) and translation (B,3):

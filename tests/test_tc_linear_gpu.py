@@ -68,3 +68,7 @@ def test_stem_implicit_gemm_matches_cudnn(N):
     assert err < 1e-2, err
     # every output row / image is written exactly once: no stale memory
     assert torch.isfinite(got.float()).all()
+    # ReLU + MaxPool2d(3, 2, 1) folded into the epilogue: equals pooling the kernel's own un-pooled output exactly
+    pooled = ops.stem_s2d_gemm(packed, w.permute(0, 2, 3, 1).reshape(64, 256), b, pool=True)
+    ref = F.max_pool2d(got.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1)
+    assert pooled.shape == (N, 64, 64, 64) and torch.equal(pooled.float(), ref)
