@@ -14,6 +14,7 @@ echo "== bench bf16"; timeout 600 python bench.py --dtype bf16 --no-posenet 2>&1
 echo "== bench f32 dist M"; timeout 600 python bench.py --dist M --no-cpu-baseline --no-e2e --no-posenet 2>&1 | tail -1
 echo "== tc_linear"; timeout 300 python tools/bench_tc_linear.py 2>&1 | tail -12
 echo "== red rates"; timeout 120 tools/_bin/red_rates 2>&1 | tail -14
+echo "== sanitizer"; for tool in memcheck racecheck initcheck synccheck; do timeout 600 compute-sanitizer --tool $tool python tools/sanitize_target.py 2>&1 | grep -E "SUMMARY|tour done" | tr '\n' ' '; echo " [$tool]"; done
 } > gpurun_out/${TAG}_log.txt 2>&1
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/${TAG}_launches.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-posenet > gpurun_out/${TAG}_ncu_bench.log 2>&1
@@ -25,7 +26,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:line
     python tools/profile_target_linear.py >> gpurun_out/${TAG}_ncu_full.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:linear_bf16_kernel -s 3 -c 1 -f -o gpurun_out/${TAG}_prof_tcl_fc1 \
     python tools/profile_target_linear.py >> gpurun_out/${TAG}_ncu_full.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"roi_crop|smallk_fused|gn_bwd|upsample2x_bwd|gn_apply|gn_stats" -f -o gpurun_out/${TAG}_prof_new \
+timeout 600 ncu --set full --clock-control none -k regex:"roi_crop|smallk_fused|gn_bwd|upsample2x_bwd|gn_apply|gn_stats|stem_s2d_gemm" -f -o gpurun_out/${TAG}_prof_new \
     python tools/profile_target_r06.py >> gpurun_out/${TAG}_ncu_full.log 2>&1
 for f in prof_bf16 prof_tcl_mem prof_tcl_fc1 prof_new; do
   ncu -i gpurun_out/${TAG}_${f}.ncu-rep --page raw --csv > gpurun_out/${TAG}_${f}_raw.csv 2>/dev/null

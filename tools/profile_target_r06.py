@@ -40,5 +40,11 @@ for _ in range(2):
     y = ops.GroupNormAct.apply(x, gamma, beta, 32, 1e-5, "gelu")
     y.backward(dy)
     ops.upsample_bilinear2x_backward(dy)
+# tcgen05 stem (implicit GEMM + fused max-pool) at 256 RoIs
+img = torch.randn(256, 3, 256, 256, generator=g).to(dev)
+packed = ops.stem_s2d_pack(img, torch.bfloat16)
+w2d = (torch.randn(64, 256, generator=g) * 0.1).bfloat16().to(dev)
+for _ in range(2):
+    ops.stem_s2d_gemm(packed, w2d, b2[:64].contiguous(), pool=True)
 torch.cuda.synchronize()
 print("done")

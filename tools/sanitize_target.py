@@ -52,6 +52,10 @@ for dtype in (torch.float32, torch.bfloat16):
                            (3, 3, 2, 2, 1, 1, 1, 1, 4, 64, 1.0))
     ops.mhsa_tokens(r(2, 64, 3 * 256).to(dev, dtype), 8)
 ops.stem_s2d_pack(r(2, 3, 32, 32).to(dev), torch.bfloat16)
+pk = ops.stem_s2d_pack(r(3, 3, 256, 256).to(dev), torch.bfloat16)
+for pool in (False, True):
+    ops.stem_s2d_gemm(pk, (r(64, 256) * 0.1).to(dev).bfloat16(), r(64).to(dev), pool=pool)
+ops.bias_add_relu_(r(2, 8, 8, 64).to(dev).bfloat16(), r(2, 8, 8, 64).to(dev).bfloat16(), r(64).to(dev))
 ops.linear_bf16(r(300, 256).to(dev).bfloat16(), r(108, 256).to(dev).bfloat16(), r(108).to(dev), "lrelu", 0.1)
 ops.pose_decode(r(5, 6).to(dev), r(5, 3).to(dev) + torch.tensor([0, 0, 2.0], device=dev), torch.tensor([[591.0, 0, 322], [0, 590, 244], [0, 0, 1]]).to(dev),
                 torch.rand(5, 2, generator=g).to(dev) * 300, torch.rand(5, 2, generator=g).to(dev) * 100 + 50, torch.rand(5, generator=g).to(dev) + 0.2)
