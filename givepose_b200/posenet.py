@@ -669,8 +669,10 @@ def _stem_s2d(img, conv, bn, dtype):
         try:
             y = ops.stem_s2d_gemm(packed, w.permute(0, 2, 3, 1).reshape(64, 256), _cached(b, torch.float32, tag="f32bias"), pool=True)
             return y.permute(0, 3, 1, 2)   # bias + ReLU + the 3x3/2 max-pool happened in the kernel's epilogue
-        except RuntimeError:
-            _stem_s2d.tc_ok = False   # e.g. the driver refuses the tensor map: cuDNN path below
+        except RuntimeError as e:
+            import warnings
+            warnings.warn(f"givepose_b200: tcgen05 stem kernel unavailable ({e}); the stem runs through cuDNN from now on")
+            _stem_s2d.tc_ok = False   # e.g. the driver refuses the tensor map: cuDNN path below (still on the device)
     x = packed.permute(0, 3, 1, 2)
     if hasattr(torch, "cudnn_convolution_relu") and _conv_bn_act.fused_ok:
         try:
