@@ -62,6 +62,8 @@ EXPORTS = {
     "gp_roi_crop": (_I, [_VP, _I, _I, _I, _VP, _VP, _I, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "gp_resize_linear_u8_normalize": (_I, [_VP, _I, _I, _I, _VP, _VP, _VP, _I, _I, _I, _VP]),
     "gp_set_tuning": (_I, [_I, _I, _I, _I]),
+    "gp_set_option": (_I, [_I, _I]),
+    "gp_get_option": (_I, [_I]),
     "gp_launch_count": (ctypes.c_uint64, []),
     "gp_launch_count_reset": (None, []),
 }

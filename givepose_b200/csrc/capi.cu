@@ -7,6 +7,7 @@
 #include <cstring>
 
 #include "dcnv3_kernels.cuh"
+#include "dcnv3_gin_binned.cuh"
 
 namespace gp {
 unsigned long long g_launches = 0;
@@ -15,6 +16,10 @@ struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 2;   // measured best on B200 (profiles/r01_sweep.md)
     int vec16 = 8;   // forward: channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
                      // backward always uses 4: its fp32 reductions then cover whole 128-byte lines per request
+    int bwd_mode = 1;              // 1: grad_offset/grad_mask kernel + binned grad_input kernel; 0: one-pass scatter kernel
+    int gin_th = 8, gin_tw = 8;    // output tile of the binned grad_input kernel
+    int gin_nt = 192;              // its CTA size
+    int fwd_mode = 1;
     bool init = false;
 };
 static Tuning g_tune;
@@ -26,6 +31,8 @@ static void init_tuning() {
     if (const char *e = getenv("GP_TILE_W")) g_tune.tile_w = atoi(e);
     if (const char *e = getenv("GP_GS")) g_tune.gs = atoi(e);
     if (const char *e = getenv("GP_VEC16")) g_tune.vec16 = atoi(e) == 4 ? 4 : 8;
+    if (const char *e = getenv("GP_BWD_MODE")) g_tune.bwd_mode = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("GP_FWD_MODE")) g_tune.fwd_mode = atoi(e) ? 1 : 0;
 }
 
 static int make_params(const gp_dcnv3_desc *d, KParams &p) {
@@ -127,14 +134,14 @@ static void launch_fwd_tile(const void *in, const void *off, const void *msk, vo
     count_launch();
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool GIN>
 static void launch_bwd_tile(const void *in, const void *off, const void *msk, const void *gout, float *gin, void *goff,
                             void *gmsk, const KParams &p, int L, cudaStream_t st) {
     const bool k3 = p.P == 9;
     const size_t sm = tile_smem(p, false);
     const unsigned grid = tile_grid(p);
 #define GP_BWD(LL, K3)                                                                                          \
-    dcnv3_bwd_tile<T, VEC, LL, K3><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, \
+    dcnv3_bwd_tile<T, VEC, LL, K3, GIN><<<grid, kTileThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, \
                                                                    (const T *)gout, gin, (T *)goff, (T *)gmsk, p)
 #define GP_BWD_L(LL) do { if (k3) GP_BWD(LL, true); else GP_BWD(LL, false); } while (0)
     switch (L) {
@@ -148,6 +155,73 @@ static void launch_bwd_tile(const void *in, const void *off, const void *msk, co
 #undef GP_BWD_L
 #undef GP_BWD
     count_launch();
+}
+
+// ---- binned grad_input (dcnv3_gin_binned.cuh) ----------------------------------------------------------------------
+// fills the tiling fields of pg (one group per CTA) and the CTA size; false: this call takes the scatter path
+static bool plan_gin_binned(const KParams &p, int dtype, KParams &pg, int *L_out, int *nt_out) {
+    if (dtype == GP_F64 || p.gc % 4) return false;
+    const int L = p.gc / 4;
+    if (L > 32 || (L & (L - 1))) return false;
+    if (p.H > 32767 || p.W > 32767) return false;
+    if ((long long)p.H * p.W * p.C * 4 >= (1ll << 31)) return false;
+    init_tuning();
+    int nt = g_tune.gin_nt;
+    if (nt != 128 && nt != 256) nt = 192;
+    if ((L != 8 && L != 16) || nt % L) nt = 192;        // the other CTA sizes are only instantiated for L = 8, 16
+    const int spt = nt == 128 ? 5 : 3;
+    auto pow2_floor = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
+    auto lg2 = [](int v) { int r = 0; while ((1 << r) < v) ++r; return r; };
+    int th = pow2_floor(g_tune.gin_th < 1 ? 1 : g_tune.gin_th), tw = pow2_floor(g_tune.gin_tw < 1 ? 1 : g_tune.gin_tw);
+    while (th * tw * p.P > nt * spt) {
+        if (th >= tw && th > 1) th /= 2; else if (tw > 1) tw /= 2; else return false;
+    }
+    pg = p;
+    pg.tile_h = th; pg.tile_w = tw; pg.gs = 1; pg.gchunks = p.G;
+    pg.lg_tw = lg2(tw); pg.lg_tp = lg2(th * tw); pg.lg_gs = 0;
+    pg.tiles_y = (p.Ho + th - 1) / th;
+    pg.tiles_x = (p.Wo + tw - 1) / tw;
+    if ((long long)p.N * pg.tiles_y * pg.tiles_x * pg.gchunks >= (1ll << 31)) return false;
+    *L_out = L;
+    *nt_out = nt;
+    return true;
+}
+
+template <typename T, int L, int NT, int SPT, int MINB>
+static cudaError_t launch_gin_one(const void *off, const void *msk, const void *gout, float *gin, const KParams &pg,
+                                  cudaStream_t st) {
+    const size_t sm = gin_binned_smem<NT, SPT>(pg.tile_h * pg.tile_w, L);
+    const unsigned grid = tile_grid(pg);
+    cudaError_t e = cudaSuccess;
+    if (pg.P == 9) {
+        auto k = dcnv3_gin_binned<T, L, NT, SPT, MINB, true>;
+        if (sm > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) k<<<grid, NT, sm, st>>>((const T *)off, (const T *)msk, (const T *)gout, gin, pg);
+    } else {
+        auto k = dcnv3_gin_binned<T, L, NT, SPT, MINB, false>;
+        if (sm > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) k<<<grid, NT, sm, st>>>((const T *)off, (const T *)msk, (const T *)gout, gin, pg);
+    }
+    count_launch();
+    return e;
+}
+
+template <typename T>
+static cudaError_t launch_gin_binned(const void *off, const void *msk, const void *gout, float *gin, const KParams &pg,
+                                     int L, int nt, cudaStream_t st) {
+    if (nt == 128 && L == 8) return launch_gin_one<T, 8, 128, 5, 8>(off, msk, gout, gin, pg, st);
+    if (nt == 128 && L == 16) return launch_gin_one<T, 16, 128, 5, 8>(off, msk, gout, gin, pg, st);
+    if (nt == 256 && L == 8) return launch_gin_one<T, 8, 256, 3, 4>(off, msk, gout, gin, pg, st);
+    if (nt == 256 && L == 16) return launch_gin_one<T, 16, 256, 3, 4>(off, msk, gout, gin, pg, st);
+    switch (L) {
+        case 1: return launch_gin_one<T, 1, 192, 3, 5>(off, msk, gout, gin, pg, st);
+        case 2: return launch_gin_one<T, 2, 192, 3, 5>(off, msk, gout, gin, pg, st);
+        case 4: return launch_gin_one<T, 4, 192, 3, 5>(off, msk, gout, gin, pg, st);
+        case 8: return launch_gin_one<T, 8, 192, 3, 5>(off, msk, gout, gin, pg, st);
+        case 16: return launch_gin_one<T, 16, 192, 3, 5>(off, msk, gout, gin, pg, st);
+        case 32: return launch_gin_one<T, 32, 192, 3, 5>(off, msk, gout, gin, pg, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <typename T, bool SOFTMAX>
@@ -234,6 +308,30 @@ int gp_set_tuning(int tile_h, int tile_w, int gs, int vec16) {
     return GP_OK;
 }
 
+int gp_set_option(int key, int value) {
+    init_tuning();
+    switch (key) {
+        case GP_OPT_BWD_MODE: if (value != 0 && value != 1) return GP_ERR_SHAPE; g_tune.bwd_mode = value; return GP_OK;
+        case GP_OPT_GIN_TILE_H: if (value < 1) return GP_ERR_SHAPE; g_tune.gin_th = value; return GP_OK;
+        case GP_OPT_GIN_TILE_W: if (value < 1) return GP_ERR_SHAPE; g_tune.gin_tw = value; return GP_OK;
+        case GP_OPT_GIN_THREADS: if (value != 128 && value != 192 && value != 256) return GP_ERR_SHAPE; g_tune.gin_nt = value; return GP_OK;
+        case GP_OPT_FWD_MODE: if (value != 0 && value != 1) return GP_ERR_SHAPE; g_tune.fwd_mode = value; return GP_OK;
+    }
+    return GP_ERR_SHAPE;
+}
+
+int gp_get_option(int key) {
+    init_tuning();
+    switch (key) {
+        case GP_OPT_BWD_MODE: return g_tune.bwd_mode;
+        case GP_OPT_GIN_TILE_H: return g_tune.gin_th;
+        case GP_OPT_GIN_TILE_W: return g_tune.gin_tw;
+        case GP_OPT_GIN_THREADS: return g_tune.gin_nt;
+        case GP_OPT_FWD_MODE: return g_tune.fwd_mode;
+    }
+    return GP_ERR_SHAPE;
+}
+
 int gp_dcnv3_forward(const void *input, const void *offset, const void *mask, void *out, const gp_dcnv3_desc *desc,
                      int dtype, void *stream) {
     return forward_impl<false>(input, offset, mask, out, desc, dtype, stream);
@@ -281,13 +379,29 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
         if (ce != cudaSuccess) return (int)ce;
     }
 
-    int L = 0, vec = 0;
-    if (plan_tiled(p, dtype, &L, &vec, true)) {
-        if (dtype == GP_F32) launch_bwd_tile<float, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else if (dtype == GP_BF16 && vec == 8) launch_bwd_tile<__nv_bfloat16, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else if (vec == 8) launch_bwd_tile<__half, 8>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
-        else launch_bwd_tile<__half, 4>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+    int L = 0, vec = 0, Lg = 0, nt = 0;
+    KParams pg;
+    init_tuning();
+    const bool split = g_tune.bwd_mode == 1 && plan_gin_binned(p, dtype, pg, &Lg, &nt);
+    if (plan_tiled(p, dtype, &L, &vec, !split)) {
+        if (split) {
+            // grad_offset / grad_mask (gathers + dot products), then grad_input (binned, no input reads)
+            if (dtype == GP_F32) launch_bwd_tile<float, 4, false>(input, offset, mask, grad_out, nullptr, grad_offset, grad_mask, p, L, st);
+            else if (dtype == GP_BF16 && vec == 8) launch_bwd_tile<__nv_bfloat16, 8, false>(input, offset, mask, grad_out, nullptr, grad_offset, grad_mask, p, L, st);
+            else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 4, false>(input, offset, mask, grad_out, nullptr, grad_offset, grad_mask, p, L, st);
+            else if (vec == 8) launch_bwd_tile<__half, 8, false>(input, offset, mask, grad_out, nullptr, grad_offset, grad_mask, p, L, st);
+            else launch_bwd_tile<__half, 4, false>(input, offset, mask, grad_out, nullptr, grad_offset, grad_mask, p, L, st);
+            ce = cudaGetLastError();
+            if (ce != cudaSuccess) return (int)ce;
+            if (dtype == GP_F32) ce = launch_gin_binned<float>(offset, mask, grad_out, (float *)acc, pg, Lg, nt, st);
+            else if (dtype == GP_BF16) ce = launch_gin_binned<__nv_bfloat16>(offset, mask, grad_out, (float *)acc, pg, Lg, nt, st);
+            else ce = launch_gin_binned<__half>(offset, mask, grad_out, (float *)acc, pg, Lg, nt, st);
+            if (ce != cudaSuccess) return (int)ce;
+        } else if (dtype == GP_F32) launch_bwd_tile<float, 4, true>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (dtype == GP_BF16 && vec == 8) launch_bwd_tile<__nv_bfloat16, 8, true>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (dtype == GP_BF16) launch_bwd_tile<__nv_bfloat16, 4, true>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else if (vec == 8) launch_bwd_tile<__half, 8, true>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
+        else launch_bwd_tile<__half, 4, true>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, p, L, st);
     } else {
         switch (dtype) {
             case GP_F32: launch_bwd_generic<float>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;

@@ -370,7 +370,8 @@ __device__ __forceinline__ void unit_reduce3(float &a, float &b, float &c, int c
     }
 }
 
-template <typename T, int VEC, int L, bool P9>
+// GIN = false: grad_offset / grad_mask only (grad_input comes from dcnv3_gin_binned, dcnv3_gin_binned.cuh)
+template <typename T, int VEC, int L, bool P9, bool GIN>
 __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks)
 dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__restrict__ msk,
                const T *__restrict__ gout, float *__restrict__ gin, T *__restrict__ goff, T *__restrict__ gmsk,
@@ -465,7 +466,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                 point_math(r, v1, v2, v3, v4, s_m, s_w_, s_h, mw);
                 char *g1 = gin_g + base * GS, *g3 = g1 + WCb * GS;
 #pragma unroll
-                for (int c4 = 0; c4 < VEC; c4 += 4) {
+                for (int c4 = 0; GIN && c4 < VEC; c4 += 4) {
                     red_add_v4(reinterpret_cast<float *>(g1) + c4, mw[0] * go[c4], mw[0] * go[c4 + 1], mw[0] * go[c4 + 2], mw[0] * go[c4 + 3]);
                     red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, mw[1] * go[c4], mw[1] * go[c4 + 1], mw[1] * go[c4 + 2], mw[1] * go[c4 + 3]);
                     red_add_v4(reinterpret_cast<float *>(g3) + c4, mw[2] * go[c4], mw[2] * go[c4 + 1], mw[2] * go[c4 + 2], mw[2] * go[c4 + 3]);
@@ -488,7 +489,7 @@ dcnv3_bwd_tile(const T *__restrict__ in, const T *__restrict__ off, const T *__r
                     point_math(r, v1, v2, v3, v4, s_m, s_w_, s_h, mw);
                     char *g1 = gin_g + bf.x * GS, *g3 = g1 + WCb * GS;
 #pragma unroll
-                    for (int c4 = 0; c4 < VEC; c4 += 4) {
+                    for (int c4 = 0; GIN && c4 < VEC; c4 += 4) {
                         if (flags & F_C1) red_add_v4(reinterpret_cast<float *>(g1) + c4, mw[0] * go[c4], mw[0] * go[c4 + 1], mw[0] * go[c4 + 2], mw[0] * go[c4 + 3]);
                         if (flags & F_C2) red_add_v4(reinterpret_cast<float *>(g1 + Cb * GS) + c4, mw[1] * go[c4], mw[1] * go[c4 + 1], mw[1] * go[c4 + 2], mw[1] * go[c4 + 3]);
                         if (flags & F_C3) red_add_v4(reinterpret_cast<float *>(g3) + c4, mw[2] * go[c4], mw[2] * go[c4 + 1], mw[2] * go[c4 + 2], mw[2] * go[c4 + 3]);

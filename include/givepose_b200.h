@@ -264,6 +264,20 @@ int gp_pose_decode(const float *rot6, const float *t, const float *cam, int cam_
  * beyond floating-point summation order. */
 int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);
 
+/* Further kernel-selection knobs (tuning sweeps and A/B measurements only; results never depend on them beyond
+ * floating-point summation order).  Returns GP_ERR_SHAPE for an unknown key / value.
+ *   GP_OPT_BWD_MODE      0 = one-pass scatter backward (one 16-byte reduction per lane per corner, round-1 kernel)
+ *                        1 = split backward (default): grad_offset/grad_mask kernel + grad_input with in-SM
+ *                            pre-aggregation (dcnv3_gin_binned: counting sort by footprint cell, register accumulation,
+ *                            one reduction per destination line of the tile's window)
+ *   GP_OPT_GIN_TILE_H/W  output tile of the binned grad_input kernel (powers of two, default 8 x 8)
+ *   GP_OPT_GIN_THREADS   its CTA size: 128, 192 (default) or 256
+ *   GP_OPT_FWD_MODE      0 = round-1 forward kernel, 1 = packed-record forward (default) */
+enum gp_option { GP_OPT_BWD_MODE = 0, GP_OPT_GIN_TILE_H = 1, GP_OPT_GIN_TILE_W = 2, GP_OPT_GIN_THREADS = 3,
+                 GP_OPT_FWD_MODE = 4 };
+int gp_set_option(int key, int value);
+int gp_get_option(int key);
+
 /* number of kernels this library has launched since load / since the last reset (bench.py's
  * `gpu_launches` is read from here, it is not an estimate) */
 uint64_t gp_launch_count(void);

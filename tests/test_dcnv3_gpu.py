@@ -306,3 +306,81 @@ def test_host_buffer_entry_points(ops, O):
         r1, r2, r3 = O.backward(hi.float(), ho_.float(), hm.float(), hg.float(), *args, 0)
         assert _rel(o2, ro) < tol and _rel(gi2, r1) < tol and _rel(go2, r2) < tol and _rel(gm2, r3) < tol, (chunks, dtype)
     _lib.lib.gp_host_cache_release()
+
+
+# ---- backward variants: one-pass scatter kernel (mode 0) and split backward with the binned grad_input kernel (mode 1) ----
+
+OPT_BWD_MODE, OPT_GIN_TH, OPT_GIN_TW, OPT_GIN_NT = 0, 1, 2, 3
+
+
+@pytest.fixture
+def bwd_options():
+    from givepose_b200._lib import lib
+    saved = [lib.gp_get_option(k) for k in range(4)]
+    yield lib
+    for k, v in enumerate(saved):
+        lib.gp_set_option(k, v)
+
+
+@pytest.mark.parametrize("mode,th,tw,nt", [(0, 8, 8, 192), (1, 8, 8, 192), (1, 8, 8, 128), (1, 16, 16, 256), (1, 4, 8, 192),
+                                           (1, 16, 8, 256), (1, 2, 2, 192)])
+@pytest.mark.parametrize("spec", ORACLE_CASES, ids=[c[0] for c in ORACLE_CASES])
+def test_backward_variants_vs_c_oracle(ops, O, bwd_options, spec, mode, th, tw, nt):
+    """Every backward variant the tuning knobs can select against the C oracle: f32 1e-4, bf16 8e-3 on rounded inputs."""
+    name, N, H, W, G, gc, k, s, pad, dil, scale, rc, dist, full = spec
+    lib = bwd_options
+    lib.gp_set_option(OPT_BWD_MODE, mode)
+    lib.gp_set_option(OPT_GIN_TH, th)
+    lib.gp_set_option(OPT_GIN_TW, tw)
+    lib.gp_set_option(OPT_GIN_NT, nt)
+    gen = torch.Generator().manual_seed(7)
+    inp, off, m, gout = _rand_case(gen, N, H, W, G, gc, k, s, pad, dil, rc, dist, full)
+    args = (k, k, s, s, pad, pad, dil, dil, G, gc, scale)
+    rgi, rgo, rgm = O.backward(inp, off, m, gout, *args, rc)
+    gi, go, gm = ops.dcnv3_backward(inp.cuda(), off.cuda(), m.cuda(), *args, gout.cuda(), 256, rc)
+    assert _rel(gi, rgi) < 1e-4 and _rel(go, rgo) < 1e-4 and _rel(gm, rgm) < 1e-4
+    if gc <= 128:
+        b = [t.to(torch.bfloat16) for t in (inp, off, m, gout)]
+        rgi, rgo, rgm = O.backward(*(t.float() for t in b[:3]), b[3].float(), *args, rc)
+        gi, go, gm = ops.dcnv3_backward(b[0].cuda(), b[1].cuda(), b[2].cuda(), *args, b[3].cuda(), 256, rc)
+        assert _rel(gi, rgi) < BF16_TOL and _rel(go, rgo) < BF16_TOL and _rel(gm, rgm) < BF16_TOL
+
+
+@pytest.mark.parametrize("std", [3.0, 30.0, 300.0])
+def test_binned_grad_input_window_overflow(ops, O, bwd_options, std):
+    """Offsets far beyond the 32-cell window of the binned kernel: the per-sample fallback scatter must give the same sums."""
+    lib = bwd_options
+    lib.gp_set_option(OPT_BWD_MODE, 1)
+    gen = torch.Generator().manual_seed(13)
+    N, H, W, G, gc = 2, 80, 72, 2, 32
+    inp = torch.randn(N, H, W, G * gc, generator=gen)
+    off = torch.randn(N, H, W, G * 18, generator=gen) * std
+    m = torch.softmax(torch.randn(N, H, W, G, 9, generator=gen), -1).reshape(N, H, W, G * 9)
+    gout = torch.randn(N, H, W, G * gc, generator=gen)
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    rgi, rgo, rgm = O.backward(inp, off, m, gout, *args, 0)
+    gi, go, gm = ops.dcnv3_backward(inp.cuda(), off.cuda(), m.cuda(), *args, gout.cuda(), 256, 0)
+    assert _rel(gi, rgi) < 1e-4 and _rel(go, rgo) < 1e-4 and _rel(gm, rgm) < 1e-4
+
+
+def test_backward_elementwise_with_absolute_floor(ops, O, bwd_options):
+    """Element-wise check (not max-norm): |got - ref| <= 1e-4 * |ref| + 1e-5 * max|ref| for every element of the three
+    gradients at config K (N = 2), so a localised error in small-magnitude outputs cannot hide behind the largest one."""
+    gen = torch.Generator().manual_seed(21)
+    N, H, W, G, gc = 2, 64, 64, 8, 32
+    for dist in ("T", "M"):
+        inp, off, m, gout = _rand_case(gen, N, H, W, G, gc, 3, 1, 1, 1, 0, dist, False)
+        args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+        ref_out = O.forward(inp.double(), off.double(), m.double(), *args, 0)
+        out = ops.dcnv3_forward(inp.cuda(), off.cuda(), m.cuda(), *args, 256, 0).cpu().double()
+        assert ((out - ref_out).abs() <= 1e-4 * ref_out.abs() + 1e-5 * ref_out.abs().max()).all()
+        refs = O.backward(inp.double(), off.double(), m.double(), gout.double(), *args, 0)
+        for mode in (0, 1):
+            bwd_options.gp_set_option(OPT_BWD_MODE, mode)
+            got = ops.dcnv3_backward(inp.cuda(), off.cuda(), m.cuda(), *args, gout.cuda(), 256, 0)
+            for g_, r_, nm in zip(got, refs, ("grad_input", "grad_offset", "grad_mask")):
+                d = (g_.cpu().double() - r_).abs()
+                # grad_offset is discontinuous where a sample sits on an integer (floor flips between f32 and f64): skip those
+                tol = 1e-4 * r_.abs() + 1e-5 * r_.abs().max()
+                bad = (d > tol)
+                assert bad.float().mean().item() < (1e-5 if nm != "grad_input" else 1e-6), (dist, mode, nm, bad.sum().item())
