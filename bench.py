@@ -104,28 +104,49 @@ class ClockSampler:
                 "power_w_max": round(max(pw), 1) if pw else None}
 
 
-def cpu_port_step(inp, off, m, gout):
-    """One fwd+bwd of the reference's CPU path as restated in oracle/dcnv3.py (dcnv3_core_pytorch + autograd)."""
-    from oracle.dcnv3 import dcnv3_core_torch
+def _reference_core():
+    """The reference's OWN ``dcnv3_core_pytorch`` (functions/dcnv3_func.py:172-220) from the files staged under the git-ignored
+    ``baseline/_ref/`` (or /root/reference where it exists): kind "reference".  Falls back to the oracle's op-for-op restatement
+    (kind "port", proven bit-identical by tests/test_oracle_golden.py) when neither is present."""
+    try:
+        from baseline import reference as R
+        return R.load_dcnv3_func().dcnv3_core_pytorch, "reference", "network/ops_dcnv3/functions/dcnv3_func.py::dcnv3_core_pytorch (reference file, staged unmodified)"
+    except Exception:
+        from oracle.dcnv3 import dcnv3_core_torch
+        return dcnv3_core_torch, "port", "oracle.dcnv3.dcnv3_core_torch (restatement of dcnv3_core_pytorch)"
+
+
+def cpu_step(core, inp, off, m, gout):
+    """One fwd+bwd of the reference's CPU path: dcnv3_core_pytorch + autograd (what network/ops_dcnv3/test.py:157-217 runs)."""
     i_, o_, m_ = (t.clone().requires_grad_(True) for t in (inp, off, m))
-    out = dcnv3_core_torch(i_, o_, m_, *ARGS, 0)
+    out = core(i_, o_, m_, *ARGS, 0)
     out.backward(gout)
     return out, i_.grad, o_.grad, m_.grad
 
 
-def time_cpu_port(n_sample, steps, warmup, dist):
+def time_cpu(n_sample, steps, warmup, dist):
+    """Median step time of the reference CPU path on all host threads.  Returns (GB/s, s/step, threads, kind, what)."""
     torch.set_num_threads(os.cpu_count() or 1)
+    core, kind, what = _reference_core()
     inp, off, m, gout = make_inputs(n_sample, dist, torch.float32, "cpu")
     for _ in range(warmup):
-        cpu_port_step(inp, off, m, gout)
+        cpu_step(core, inp, off, m, gout)
     ts = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_port_step(inp, off, m, gout)
+        cpu_step(core, inp, off, m, gout)
         ts.append(time.perf_counter() - t0)
     fwd, bwd = alg_bytes(n_sample, 64, 64, 256, 8, 9, 64, 64, 4)
-    dt = sum(ts) / len(ts)
-    return (fwd + bwd) / dt / 1e9, dt, torch.get_num_threads()
+    dt = statistics.median(ts)
+    return (fwd + bwd) / dt / 1e9, dt, torch.get_num_threads(), kind, what
+
+
+def bench_config(world, dist, esz=4):
+    """`config` of the bench line -- identical in both arms (the reference arm times the same N = 64 fp32 workload)."""
+    fwd_b, bwd_b = alg_bytes(CFG["N"], 64, 64, 256, 8, 9, 64, 64, esz)
+    return {"workload": "DCNv3 core fwd+bwd, N=64 RoIs per GPU, 64x64x256 channel-last, group=8, 3x3 s1 p1 (BASELINE configs[1])",
+            "dist": dist, "parallelism": f"roi-shard x{world}, no collective",
+            "l2": "no flush needed: 763 MB of inputs per step >> 126 MB L2", "algorithmic_bytes_per_step": fwd_b + bwd_b}
 
 
 def time_reference_cuda(inp, off, m, gout, dtype_name, timed, reps, ms_fwd, ms_bwd):
@@ -152,6 +173,82 @@ def time_reference_cuda(inp, off, m, gout, dtype_name, timed, reps, ms_fwd, ms_b
         return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
 
 
+class numa_local:
+    """Context manager: run the enclosed host-buffer allocations on the CPUs of the NUMA node the rank's GPU hangs off, so
+    that first-touch places the pinned pages next to that GPU's PCIe root (8 ranks uploading from one node's memory was the
+    r01 e2e bottleneck).  Restores the affinity afterwards (the CPU baseline wants every core).  Best effort: a missing
+    sysfs entry leaves the affinity untouched; `info` says what happened."""
+
+    def __init__(self, dev_index):
+        self.idx, self.old, self.info = dev_index, None, {"numa_node": None}
+
+    def __enter__(self):
+        try:
+            pr = torch.cuda.get_device_properties(self.idx)
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+            node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+            self.info = {"numa_node": node, "pci": bdf}
+            if node >= 0:
+                cpus = set()
+                for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                    a, _, b = part.partition("-")
+                    cpus.update(range(int(a), int(b or a) + 1))
+                self.old = os.sched_getaffinity(0)
+                use = cpus & self.old
+                if use:
+                    os.sched_setaffinity(0, use)
+                    self.info["cpus"] = len(use)
+        except Exception as e:   # noqa: BLE001 -- informational only
+            self.info["note"] = f"{type(e).__name__}: {str(e)[:80]}"
+        return self
+
+    def __exit__(self, *exc):
+        if self.old:
+            os.sched_setaffinity(0, self.old)
+        return False
+
+
+def pcie_probe(dev, barrier, mb=256):
+    """H2D and D2H bandwidth of one pinned buffer per rank, all ranks copying at the same time (barrier before each
+    direction): the measured ceiling the host-buffer e2e numbers run against.  CUDA events, GB/s per GPU."""
+    n = mb << 20
+    h = torch.empty(n, dtype=torch.uint8).pin_memory()
+    d = torch.empty(n, dtype=torch.uint8, device=dev)
+    out = {}
+    for name, (dst, src) in (("h2d", (d, h)), ("d2h", (h, d))):
+        dst.copy_(src, non_blocking=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        b.record()
+        barrier()
+        out[name + "_GBps"] = round(4 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+    return out
+
+
+def measured_ceilings(dist, dtype_name):
+    """Speed of light of the sampling kernels' ACCESS PATTERN on this GPU, measured by tools/micro/gather_rates.cu (36
+    precomputed line gathers + 1 store per unit and nothing else; 36 line reductions per unit and nothing else): the ceiling
+    the decomposition can reach, as opposed to the HBM roofline the contract's `frac` is quoted against."""
+    exe = os.path.join(ROOT, "tools", "_bin", "gather_rates")
+    if not os.path.exists(exe):
+        return {"unavailable": "tools/_bin/gather_rates not built (python -c 'import __graft_entry__ as g; g.build()')"}
+    try:
+        import re
+        txt = subprocess.run([exe], capture_output=True, text=True, timeout=180).stdout
+        ms = {}
+        for mm in re.finditer(r"gather mode (\d) dist (\w)\s+(.*?)\s+([\d.]+) ms", txt):
+            ms[(int(mm.group(1)), mm.group(2))] = float(mm.group(4))
+        g = ms.get((0, dist)) if dtype_name == "f32" else min(v for (k, d_), v in ms.items() if k in (1, 2) and d_ == dist)
+        return {"source": "tools/micro/gather_rates.cu, same run, same GPU", "gather_only_fwd_ms": g,
+                "gather_no_records_ms": ms.get((3, "T")), "scatter_only_ms": ms.get((5, dist)),
+                "gather_plus_scatter_ms": ms.get((6, dist))}
+    except Exception as e:   # noqa: BLE001 -- a micro-benchmark must never take the bench down
+        return {"unavailable": f"{type(e).__name__}: {str(e)[:120]}"}
+
+
 # ---- PoseNet RoIs/s (BASELINE configs[2..3]) ---------------------------------------------------------------
 # per-RoI algorithmic FLOPs (2*MAC, SURVEY.md 8(d) D4): decoders 12.99 + 12.84 G, MAPEncoder 1.40 G, ConvPnPNet 0.14 G,
 # feat_reducer 0.034 G, ResNet-34 trunk @256^2 ~ 7.34 G (+ neck 0.067 G)
@@ -176,21 +273,33 @@ def posenet_inputs(B, seed):
 
 
 def time_posenet_cpu(B, steps):
-    """Reference CPU path (oracle port of PoseNet.forward) on all host threads; returns RoIs/s."""
+    """Reference CPU path of PoseNet.forward on all host threads; returns (RoIs/s, median s/batch, threads, kind, what).
+    kind "reference": the reference's own network/PoseNet.py (staged files + leaf stubs, baseline/reference.py) with the oracle's
+    seeded weights loaded strict=True; "port": the oracle restatement when the reference files are not available."""
     from oracle import posenet as OP
     torch.set_num_threads(os.cpu_count() or 1)
     ora = OP.PoseNet().eval()
     OP.init_weights(ora, "o1", seed=0)
     data = OP.make_inputs(B, seed=0)
+    kind, what = "port", "oracle.posenet.PoseNet.forward (restatement)"
+    fwd = lambda: ora(data)
+    try:
+        from baseline import reference as R
+        _, ref = R.reference_posenet_cpu()
+        ref.load_state_dict(ora.state_dict(), strict=True)
+        fwd = lambda: ref.forward({k: v.clone() for k, v in data.items()}, "cpu")
+        kind, what = "reference", "reference network/PoseNet.py::PoseNet.forward (staged unmodified; ResNet-34 stand-in backbone, dcnv3_core_pytorch core)"
+    except Exception:
+        pass
     with torch.no_grad():
-        ora(data)
+        fwd()
         ts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            ora(data)
+            fwd()
             ts.append(time.perf_counter() - t0)
-    dt = sum(ts) / len(ts)
-    return B / dt, dt, torch.get_num_threads()
+    dt = statistics.median(ts)
+    return B / dt, dt, torch.get_num_threads(), kind, what
 
 
 def run_posenet(args, rank, world, dev, dist):
@@ -212,11 +321,11 @@ def run_posenet(args, rank, world, dev, dist):
     host = posenet_inputs(B, seed=rank)                      # this rank's shard, generated on the host
     pinned = {k: v.pin_memory() for k, v in host.items()}
     resident = {k: v.to(dev) for k, v in host.items()}
-    for prec in (["bf16", "fp32"] if args.posenet_fp32 else ["bf16"]):
+    for prec in (["bf16"] if args.no_posenet_fp32 else ["bf16", "fp32"]):
         _, net = build_posenet(prec, dev)
         steps = args.posenet_steps if prec == "bf16" else max(1, args.posenet_steps // 3)
         with torch.no_grad():
-            for _ in range(3):
+            for _ in range(3 if prec == "bf16" else 1):
                 net(resident, dev)
             barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -318,14 +427,20 @@ def run_posenet(args, rank, world, dev, dist):
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         ms, ms_e2e = t.item(), te.item() * 1e3
         nb = lambda x: x.numel() * x.element_size()
+        e2e_crops = {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "RoIs/s", "ms_per_batch": round(ms_e2e, 3),
+                     "h2d_bytes_per_step": sum(nb(v) for v in host.values()) * world,
+                     "d2h_bytes_per_step": sum(nb(x) for x in pose) * world,
+                     "api": "givepose_b200.posenet.PoseNet.forward(fp32 RoI crops on pinned host memory, device)"}
         entry = {"value": round(total / (ms * 1e-3), 1), "ms_per_batch": round(ms, 3), "steps": steps,
-                 "tflops": round(total / (ms * 1e-3) * POSENET_GFLOP_PER_ROI / 1e3, 1),
-                 "e2e": {"value": round(total / (ms_e2e * 1e-3), 1), "unit": "RoIs/s", "ms_per_batch": round(ms_e2e, 3),
-                         "h2d_bytes_per_step": sum(nb(v) for v in host.values()) * world,
-                         "d2h_bytes_per_step": sum(nb(x) for x in pose) * world,
-                         "api": "givepose_b200.posenet.PoseNet.forward(data on pinned host memory, device)"}}
+                 "tflops": round(total / (ms * 1e-3) * POSENET_GFLOP_PER_ROI / 1e3, 1)}
         if img_in is not None:
-            entry["e2e_image_in"] = img_in
+            # the end-to-end number of the PoseNet section: camera frames in -> poses out (7x fewer host bytes than
+            # pre-cropped fp32 RoIs, which saturate the host side at 8 ranks); the host-crops variant stays beside it
+            img_in["d2h_bytes_per_step"] = e2e_crops["d2h_bytes_per_step"]
+            entry["e2e"] = img_in
+            entry["e2e_host_crops"] = e2e_crops
+        else:
+            entry["e2e"] = e2e_crops
         if latency is not None:
             entry["latency_8_rois"] = latency
         if prec == "bf16":
@@ -334,8 +449,12 @@ def run_posenet(args, rank, world, dev, dist):
             entry["roofline"] = {"bound": "tensor", "achieved": entry["tflops"], "peak": peak * world, "unit": "TFLOP/s",
                                  "frac": round(entry["tflops"] / (peak * world), 4),
                                  "note": "whole forward (library convs/GEMMs + our glue kernels) vs sustained bf16 GEMM peak"}
-            out.update({"value": entry["value"], "dtype": "bf16", **{k: v for k, v in entry.items() if k != "value"}})
+            out.update({"value": entry["value"], "value_bf16": entry["value"], "dtype": "bf16",
+                        "dtype_note": "value / value_bf16: bf16 weights + activations, fp32 accumulation (stated tolerance: "
+                                      "tests/test_posenet_gpu.py BF16_*); value_fp32: the 1e-4 parity mode (TF32 off)",
+                        **{k: v for k, v in entry.items() if k != "value"}})
         else:
+            out["value_fp32"] = entry["value"]
             out["fp32_parity_mode"] = entry
         del net
         torch.cuda.empty_cache()
@@ -399,27 +518,28 @@ def run_posenet(args, rank, world, dev, dist):
         del net, opt, bucket
         torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rps, dt, threads = time_posenet_cpu(8, 2)
-        out["cpu_baseline"] = {"value": round(rps, 3), "unit": "RoIs/s", "cores": threads, "kind": "port",
-                               "sample": f"oracle.posenet.PoseNet.forward (fp32, CPU), B=8 RoIs, 1 warm-up + 2 timed, {dt:.2f} s/batch"}
+        rps, dt, threads, kind, what = time_posenet_cpu(64, 3)
+        out["cpu_baseline"] = {"value": round(rps, 3), "unit": "RoIs/s", "cores": threads, "kind": kind,
+                               "sample": f"{what}, fp32, B=64 RoIs, 1 warm-up + median of 3 timed, {dt:.2f} s/batch"}
     return out
 
 
 def run_reference(args, rank):
-    """Reference arm: the reference's CPU implementation of the path (oracle port; the Python reference cannot
-    travel to the GPU box and its CUDA extension has no CPU path, src/dcnv3.h:37) on rank 0, all host threads."""
+    """Reference arm: the reference's OWN CPU implementation of the path -- dcnv3_core_pytorch + autograd from the reference
+    file staged under baseline/_ref/ (kind "reference"; the oracle port only if the staged files are missing) -- on rank 0 with
+    all host threads, on the SAME workload as our arm (N = 64 RoIs per step), median over the timed steps."""
     if rank != 0:
         return
-    n_sample = 8   # BASELINE configs[0]: N=8
-    gbps, dt, threads = time_cpu_port(n_sample, max(1, args.steps), max(1, min(args.warmup, 2)), args.dist)
+    n_sample = CFG["N"]
+    steps, warm = max(1, args.steps), max(1, min(args.warmup, 2))
+    gbps, dt, threads, kind, what = time_cpu(n_sample, steps, warm, args.dist)
     line = {
         "impl": "reference", "metric": METRIC, "value": round(gbps, 4), "unit": "GB/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
+        "steps": steps, "warmup": warm, "ms_per_step": round(dt * 1e3, 3), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "DCNv3 core fwd+bwd, 64x64x256 channel-last, group=8, 3x3 s1 p1 (BASELINE configs[1])",
-                   "dist": args.dist, "sample": f"N={n_sample} RoIs per step (bounded sample of the N=64 workload)"},
-        "cpu_baseline": {"value": round(gbps, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle.dcnv3.dcnv3_core_torch fwd + autograd bwd, N={n_sample}, fp32, {threads} threads"},
+        "config": bench_config(args.gpus, args.dist),
+        "cpu_baseline": {"value": round(gbps, 4), "unit": "GB/s", "cores": threads, "kind": kind,
+                         "sample": f"{what} fwd + autograd bwd, N={n_sample} (the full workload), fp32, {threads} threads, median of {steps} steps"},
         "e2e": {"value": round(gbps, 4), "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -441,10 +561,10 @@ def run_reference(args, rank):
         line["reference_cuda_kernels"] = {k: v for k, v in rc.items() if not k.startswith(("ours", "speedup"))}
         del inp, off, m, gout
     if not args.no_posenet:
-        rps, dtp, th = time_posenet_cpu(8, max(1, min(args.steps, 3)))
+        rps, dtp, th, pkind, pwhat = time_posenet_cpu(64, 3)
         line["posenet"] = {"metric": "posenet_inference_rois_per_s", "value": round(rps, 3), "unit": "RoIs/s", "dtype": "f32",
-                           "cpu_baseline": {"value": round(rps, 3), "unit": "RoIs/s", "cores": th, "kind": "port",
-                                            "sample": f"oracle.posenet.PoseNet.forward on CPU, B=8 RoIs per step, {dtp:.2f} s/step"},
+                           "cpu_baseline": {"value": round(rps, 3), "unit": "RoIs/s", "cores": th, "kind": pkind,
+                                            "sample": f"{pwhat}, B=64 RoIs per step, median of 3, {dtp:.2f} s/step"},
                            "e2e": {"value": round(rps, 3), "unit": "RoIs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -459,10 +579,12 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-ceilings", action="store_true", help="skip the access-pattern micro-benchmark (tools/_bin/gather_rates)")
     ap.add_argument("--no-posenet", action="store_true", help="skip the PoseNet RoIs/s section")
     ap.add_argument("--posenet-rois", type=int, default=4096, help="RoIs per batch, sharded across the ranks (BASELINE configs[3])")
     ap.add_argument("--posenet-steps", type=int, default=5)
-    ap.add_argument("--posenet-fp32", action="store_true", help="also time the fp32 (TF32 off) parity mode")
+    ap.add_argument("--posenet-fp32", action="store_true", help="(default now) also time the fp32 (TF32 off) parity mode")
+    ap.add_argument("--no-posenet-fp32", action="store_true", help="skip the fp32 parity-mode timing of PoseNet")
     ap.add_argument("--train-rois", type=int, default=48, help="RoIs per GPU of the training-step config (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -548,9 +670,13 @@ def main():
     # ---- e2e: host buffers through the C ABI, copies inside the timed region -----------------------------
     e2e = None
     if not args.no_e2e:
-        hin, hoff, hm, hgo = (x.cpu().pin_memory() for x in (inp, off, m, gout))
-        hout = torch.empty_like(hgo).pin_memory()
-        hgi, hgoff, hgm = torch.empty_like(hin).pin_memory(), torch.empty_like(hoff).pin_memory(), torch.empty_like(hm).pin_memory()
+        with numa_local(local_rank) as numa:   # pinned host buffers next to this rank's GPU
+            hin, hoff, hm, hgo = (x.cpu().pin_memory() for x in (inp, off, m, gout))
+            hout = torch.empty_like(hgo).pin_memory()
+            hgi, hgoff, hgm = torch.empty_like(hin).pin_memory(), torch.empty_like(hoff).pin_memory(), torch.empty_like(hm).pin_memory()
+            for t_ in (hout, hgi, hgoff, hgm):
+                t_.zero_()                      # first touch on the local node
+            probe = pcie_probe(dev, barrier)
         d = _lib.DCNv3Desc(N, 64, 64, 8, 32, 3, 3, 1, 1, 1, 1, 1, 1, 0, 64, 64, 1.0)
         dt_code = _lib.GP_F32 if args.dtype == "f32" else _lib.GP_BF16
         vp = lambda x: ctypes.c_void_p(x.data_ptr())
@@ -572,9 +698,18 @@ def main():
         nb = lambda x: x.numel() * x.element_size()
         h2d = nb(hin) + nb(hoff) + nb(hm) + nb(hgo)
         d2h = nb(hout) + nb(hgi) + nb(hgoff) + nb(hgm)
+        pr = torch.tensor([probe["h2d_GBps"], probe["d2h_GBps"]], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(pr, op=dist.ReduceOp.MIN)
         e2e = {"value": round((fwd_b + bwd_b) * world / t_e2e.item() / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(t_e2e.item() * 1e3, 3),
-               "steps": e2e_steps, "api": "gp_dcnv3_forward_backward_host (pinned host buffers, inputs uploaded once, 8 RoI chunks pipelined H2D | kernels | D2H)"}
+               "steps": e2e_steps, "api": "gp_dcnv3_forward_backward_host (pinned host buffers, inputs uploaded once, 8 RoI chunks pipelined H2D | kernels | D2H)",
+               # the limiting resource, measured: each rank moves h2d bytes up and d2h bytes down per step over ITS PCIe link,
+               # all ranks at once out of host memory; `pcie_probe` is the plain pinned-copy rate under the same concurrency
+               "pcie": {"per_gpu_h2d_GBps": round(h2d / t_e2e.item() / 1e9, 1), "per_gpu_d2h_GBps": round(d2h / t_e2e.item() / 1e9, 1),
+                        "probe_min_over_ranks": {"h2d_GBps": round(pr[0].item(), 1), "d2h_GBps": round(pr[1].item(), 1), "concurrent_ranks": world},
+                        "host_buffers": numa.info,
+                        "bound": "host: PCIe / host-memory bandwidth (1.5 GB up + 1.5 GB down per rank per step against 2 ms of kernels)"}}
         lib.gp_host_cache_release()
 
     posenet = None
@@ -610,12 +745,21 @@ def main():
                         "frac": round(fwd_b / (ms_fwd * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": fwd_b, "ms": round(ms_fwd, 4)},
                 "fwd_bwd_frac": round((fwd_b + bwd_b) / ((ms_fwd + ms_bwd) * 1e-3) / 1e9 / peak, 4)}
 
+    if world == 1 and not args.no_ceilings:
+        ceil = measured_ceilings(args.dist, args.dtype)
+        roofline["measured_ceilings"] = ceil
+        if ceil.get("gather_only_fwd_ms"):
+            # secondary keys (the contract's `frac` stays the HBM fraction): how close each kernel runs to the measured speed of
+            # light of its own access pattern -- L1 line gathers for the forward, gathers + L2 line reductions for the backward
+            roofline["fwd"]["l1_gather_ceiling_frac"] = round(ceil["gather_only_fwd_ms"] / ms_fwd, 3)
+            if ceil.get("gather_plus_scatter_ms"):
+                roofline["l2_red_ceiling_frac"] = round(ceil["gather_plus_scatter_ms"] / ms_bwd, 3)
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        n_s = 8
-        gbps, dt_cpu, threads = time_cpu_port(n_s, 3, 1, args.dist)
-        cpu = {"value": round(gbps, 4), "unit": "GB/s", "cores": threads, "kind": "port",
-               "sample": f"oracle.dcnv3.dcnv3_core_torch fwd + autograd bwd, N={n_s} of 64 RoIs, fp32, 1 warm-up + 3 timed, "
+        n_s = CFG["N"]
+        gbps, dt_cpu, threads, kind, what = time_cpu(n_s, 3, 1, args.dist)
+        cpu = {"value": round(gbps, 4), "unit": "GB/s", "cores": threads, "kind": kind,
+               "sample": f"{what} fwd + autograd bwd, N={n_s} RoIs (the full workload), fp32, 1 warm-up + median of 3 timed, "
                          f"{dt_cpu * 1e3:.1f} ms/step"}
 
     # the reference's OWN CUDA kernels (oracle/_ref/DCNv3_ref.so, built unmodified by oracle/build_ref_ext.py) on this
@@ -628,10 +772,7 @@ def main():
         "metric": METRIC, "value": round(value, 2), "unit": "GB/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
-        "config": {"workload": "DCNv3 core fwd+bwd, N=64 RoIs per GPU, 64x64x256 channel-last, group=8, 3x3 s1 p1 "
-                               "(BASELINE configs[1])", "dist": args.dist, "parallelism": f"roi-shard x{world}, no collective",
-                   "l2": "no flush needed: 763 MB of inputs per step >> 126 MB L2",
-                   "algorithmic_bytes_per_step": fwd_b + bwd_b},
+        "config": bench_config(world, args.dist, esz),
         "roofline": roofline, "cpu_baseline": cpu, "reference_cuda_kernels": ref_cuda, "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "posenet": posenet,
         "wall_s_timed_region": round(t_wall, 3),
     }

@@ -33,6 +33,7 @@ EXPORTS = {
     "gp_dcnv3_out_size": (_I, [_I, _I, _I, _I, _I]),
     "gp_dcnv3_forward": (_I, [_VP, _VP, _VP, _VP, _DP, _I, _VP]),
     "gp_dcnv3_forward_softmax": (_I, [_VP, _VP, _VP, _VP, _DP, _I, _VP]),
+    "gp_dcnv3_forward_softmax_packed": (_I, [_VP, _VP, _VP, ctypes.c_longlong, _DP, _I, _VP]),
     "gp_dcnv3_backward_workspace": (_SZ, [_DP, _I]),
     "gp_dcnv3_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _SZ, _VP, _SZ, _DP, _I, _VP]),
     "gp_dcnv3_sample_index": (_I, [_VP, _VP, _VP, _DP, _I, _VP]),

@@ -16,7 +16,7 @@ struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 2;   // measured best on B200 (profiles/r01_sweep.md)
     int vec16 = 8;   // forward: channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
                      // backward always uses 4: its fp32 reductions then cover whole 128-byte lines per request
-    int bwd_mode = 1;              // 1: grad_offset/grad_mask kernel + binned grad_input kernel; 0: one-pass scatter kernel
+    int bwd_mode = 0;              // 0: one-pass scatter kernel (fastest measured, profiles/r02a_*); 1: grad_offset/grad_mask kernel + binned grad_input kernel
     int gin_th = 8, gin_tw = 8;    // output tile of the binned grad_input kernel
     int gin_nt = 192;              // its CTA size
     int fwd_mode = 1;
@@ -58,6 +58,8 @@ static int make_params(const gp_dcnv3_desc *d, KParams &p) {
     p.scale = d->offset_scale;
     p.n_units = (long long)d->N * d->Ho * d->Wo * d->G;
     if (p.P <= 0) return GP_ERR_SHAPE;
+    p.off_q = (long long)p.G * p.P * 2;
+    p.msk_q = (long long)p.G * p.P;
     return GP_OK;
 }
 
@@ -243,16 +245,22 @@ static void launch_bwd_generic(const void *in, const void *off, const void *msk,
     count_launch();
 }
 
+// pitch > 0: `off` points at packed rows [G*P*2 offsets | G*P mask values | padding] of `pitch` elements per pixel
 template <bool SOFTMAX>
 static int forward_impl(const void *in, const void *off, const void *msk, void *out, const gp_dcnv3_desc *d, int dtype,
-                        void *stream) {
+                        void *stream, long long pitch = 0) {
     if (!in || !off || !msk || !out) return GP_ERR_NULL;
     if (!elem_size(dtype)) return GP_ERR_DTYPE;
     KParams p;
     if (int e = make_params(d, p)) return e;
-    if (!aligned16(in) || !aligned16(off) || !aligned16(msk) || !aligned16(out)) return GP_ERR_ALIGN;
+    if (!aligned16(in) || !aligned16(off) || !aligned16(out) || (!pitch && !aligned16(msk))) return GP_ERR_ALIGN;
+    if (pitch) {
+        if (pitch < (long long)p.G * p.P * 3 || pitch % 2) return GP_ERR_SHAPE;   // (w, h) pairs are read as one 2-element word
+        p.off_q = p.msk_q = pitch;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     int L = 0, vec = 0;
+    if (pitch && !plan_tiled(p, dtype, &L, &vec)) return GP_ERR_UNSUPPORTED;   // packed rows: tiled kernels only
     if (plan_tiled(p, dtype, &L, &vec)) {
         if (dtype == GP_F32) launch_fwd_tile<float, 4, SOFTMAX>(in, off, msk, out, p, L, st);
         else if (dtype == GP_BF16 && vec == 8) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
@@ -340,6 +348,15 @@ int gp_dcnv3_forward(const void *input, const void *offset, const void *mask, vo
 int gp_dcnv3_forward_softmax(const void *input, const void *offset, const void *mask_logits, void *out,
                              const gp_dcnv3_desc *desc, int dtype, void *stream) {
     return forward_impl<true>(input, offset, mask_logits, out, desc, dtype, stream);
+}
+
+int gp_dcnv3_forward_softmax_packed(const void *input, const void *offset_mask, void *out, long long pitch,
+                                    const gp_dcnv3_desc *desc, int dtype, void *stream) {
+    if (!offset_mask || !desc || pitch <= 0) return GP_ERR_NULL;
+    const size_t es = elem_size(dtype);
+    if (!es) return GP_ERR_DTYPE;
+    const char *msk = (const char *)offset_mask + (size_t)desc->G * (desc->kh * desc->kw - desc->remove_center) * 2 * es;
+    return forward_impl<true>(input, offset_mask, msk, out, desc, dtype, stream, pitch);
 }
 
 size_t gp_dcnv3_backward_workspace(const gp_dcnv3_desc *desc, int dtype) {
@@ -466,6 +483,13 @@ cudaError_t hc_get(int slot, size_t bytes, void **out) {
     return cudaSuccess;
 }
 
+// RAII: the *_host entry points run on `device` and hand the caller's current device back on every return path
+struct DeviceGuard {
+    int prev = -1;
+    DeviceGuard() { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 cudaError_t hc_begin(int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return e;
@@ -509,6 +533,7 @@ int gp_dcnv3_forward_host(const void *h_input, const void *h_offset, const void 
     const size_t n_in = (size_t)p.N * p.H * p.W * p.C, n_out = (size_t)p.N * p.Ho * p.Wo * p.C;
     const size_t n_off = (size_t)p.n_units * p.P * 2, n_msk = (size_t)p.n_units * p.P;
     if (offset_elems < n_off || mask_elems < n_msk) return GP_ERR_SHAPE;
+    DeviceGuard guard_;
     GP_CUDA(hc_begin(device));
     void *d_in, *d_off, *d_msk, *d_out;
     GP_CUDA(hc_get(0, n_in * es, &d_in));
@@ -537,6 +562,7 @@ int gp_dcnv3_backward_host(const void *h_input, const void *h_offset, const void
     const size_t n_in = (size_t)p.N * p.H * p.W * p.C, n_out = (size_t)p.N * p.Ho * p.Wo * p.C;
     const size_t n_off = (size_t)p.n_units * p.P * 2, n_msk = (size_t)p.n_units * p.P;
     if (offset_elems < n_off || mask_elems < n_msk) return GP_ERR_SHAPE;
+    DeviceGuard guard_;
     GP_CUDA(hc_begin(device));
     void *d_in, *d_off, *d_msk, *d_go, *d_gi, *d_goff, *d_gmsk, *d_ws = nullptr;
     GP_CUDA(hc_get(0, n_in * es, &d_in));
@@ -582,6 +608,7 @@ int gp_dcnv3_forward_backward_host(const void *h_input, const void *h_offset, co
     if (chunks < 1) chunks = 1;
     if (chunks > 64) chunks = 64;
     if (chunks > p.N) chunks = p.N;
+    DeviceGuard guard_;
     GP_CUDA(hc_begin(device));
     if (!g_hc.s_h2d) GP_CUDA(cudaStreamCreateWithFlags(&g_hc.s_h2d, cudaStreamNonBlocking));
     if (!g_hc.s_d2h) GP_CUDA(cudaStreamCreateWithFlags(&g_hc.s_d2h, cudaStreamNonBlocking));
@@ -599,7 +626,17 @@ int gp_dcnv3_forward_backward_host(const void *h_input, const void *h_offset, co
     GP_CUDA(hc_get(6, n_msk * es, (void **)&d_gmsk));
     const bool half16 = dtype == GP_BF16 || dtype == GP_F16;
     // slot 7: [forward output | fp32 workspace of the 16-bit backward (one chunk)]
-    const int per = (p.N + chunks - 1) / chunks;
+    int per = (p.N + chunks - 1) / chunks;
+    // every chunk's device pointers must stay 16-byte aligned (gp_dcnv3_forward / backward require it): round the chunk
+    // size up to the smallest RoI count whose offset / mask / image slices are multiples of 16 bytes (<= 16 RoIs)
+    {
+        int q = 1;
+        while (q < 16 && (((size_t)q * img_msk * es) % 16 || ((size_t)q * img_off * es) % 16 || ((size_t)q * img_in * es) % 16 ||
+                          ((size_t)q * img_out * es) % 16))
+            ++q;
+        per = ((per + q - 1) / q) * q;
+        if (((size_t)per * img_msk * es) % 16 || ((size_t)per * img_in * es) % 16 || ((size_t)per * img_out * es) % 16) per = p.N;   // one chunk
+    }
     const size_t ws_chunk = half16 ? img_in * per * sizeof(float) : 0;
     GP_CUDA(hc_get(7, img_out * p.N * es + ws_chunk + 256, (void **)&d_out));
     char *d_ws = half16 ? d_out + ((img_out * p.N * es + 255) / 256) * 256 : nullptr;

@@ -110,8 +110,8 @@ __device__ __forceinline__ void build_records(const T *__restrict__ off, const T
             continue;
         }
         const long long q = ((long long)t.b * p.Ho + oh) * p.Wo + ow;
-        const long long row = (q * p.G + t.g0 + gl) * (long long)P;   // (q*G+g)*P, cuh:243-244
-        const T *orow = off + 2 * row, *mrow = msk + row;
+        // dense rows: (q*G+g)*P, cuh:243-244 (off_q = G*P*2, msk_q = G*P); packed offset||logits rows share one pitch
+        const T *orow = off + q * p.off_q + (t.g0 + gl) * (P * 2), *mrow = msk + q * p.msk_q + (t.g0 + gl) * P;
         const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
         const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
         float mx = 0.f, inv = 1.f;

@@ -31,6 +31,10 @@ struct KParams {
     int tile_h, tile_w, tiles_y, tiles_x, gs /*groups per CTA*/, gchunks /*G/gs*/;   // tile_h, tile_w, gs: powers of two
     int lg_tw, lg_tp, lg_gs; // log2(tile_w), log2(tile_h*tile_w), log2(gs)
     long long n_units;       // N*Ho*Wo*G
+    // offset / mask row addressing of the tiled forward: offset row of (q, g) starts at off + q*off_q + g*P*2, mask row at
+    // msk + q*msk_q + g*P.  Dense tensors (the reference layout, cuh:243-244): off_q = G*P*2, msk_q = G*P.  The packed
+    // offset||mask-logits rows of gp_dcnv3_forward_softmax_packed use one pitch for both.
+    long long off_q, msk_q;
 };
 
 template <typename T> struct AccOf { using type = float; };

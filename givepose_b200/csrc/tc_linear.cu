@@ -569,20 +569,23 @@ static bool make_im2col_map(CUtensorMap *map, const void *ptr, long long n_pixel
 }  // namespace tc
 }  // namespace gp
 
+constexpr int kMaxDevices = 64;
+
 template <int BN, int ACT>
 static int launch_linear(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, float slope, cudaStream_t st) {
     using namespace gp::tc;
     using C = Cfg<BN>;
-    static bool attr_set = false;
-    static int sms = 0;
-    if (!attr_set) {
+    // the opt-in shared-memory size is a per-device function attribute and the grid is one CTA per SM of THAT device
+    static int sms_of[kMaxDevices] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return GP_ERR_UNSUPPORTED;
+    if (!sms_of[dev]) {
         cudaError_t e = cudaFuncSetAttribute(linear_bf16_kernel<BN, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     }
+    const int sms = sms_of[dev];
     CUtensorMap mx, mw;
     if (!make_map(&mx, x, M, K, BM) || !make_map(&mw, w, N, K, BN)) return GP_ERR_UNSUPPORTED;
     const long long tiles = (long long)((N + BN - 1) / BN) * ((M + BM - 1) / BM);
@@ -622,17 +625,17 @@ extern "C" int gp_stem_s2d_gemm(const void *packed, const void *w, const float *
     if (N <= 0 || Ho <= 0 || Wo != BM) return GP_ERR_UNSUPPORTED;   // one 128-pixel output row per tile (256 x 256 crops)
     if ((reinterpret_cast<uintptr_t>(packed) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
     if ((long long)N * Hp * Wp >= (1ll << 31)) return GP_ERR_SHAPE;
-    static bool attr_set = false;
-    static int sms = 0;
-    if (!attr_set) {
+    static int sms_of[kMaxDevices] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return GP_ERR_UNSUPPORTED;
+    if (!sms_of[dev]) {
         cudaError_t e = cudaFuncSetAttribute(stem_s2d_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(stem_s2d_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stem::SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        attr_set = true;
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     }
+    const int sms = sms_of[dev];
     CUtensorMap mv, mw;
     if (!make_im2col_map(&mv, packed, (long long)N * Hp * Wp) || !make_map(&mw, w, stem::BN, stem::TAPS * BK, stem::BN)) return GP_ERR_UNSUPPORTED;
     const int items = N * ((Ho + stem::ROWS_PER_ITEM - 1) / stem::ROWS_PER_ITEM);

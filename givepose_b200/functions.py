@@ -91,6 +91,26 @@ def dcnv3_forward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, p
     return out
 
 
+def dcnv3_forward_packed(input, offset_mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
+                         group, group_channels, offset_scale, im2col_step, remove_center=0):
+    """``dcnv3_forward(..., mask_is_logits=True)`` with offsets and mask logits packed in the rows of ONE tensor
+    ``offset_mask`` (rows, pitch): ``[G*P*2 offsets | G*P logits | padding]`` -- the output of the fused offset||mask Linear
+    (``modules/dcnv3.py:330-334``), consumed without splitting it into two contiguous tensors."""
+    dt = _validate((("input", input), ("offset_mask", offset_mask)), input, group, group_channels, im2col_step)
+    d, Ho, Wo, P = _desc(input, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w, group,
+                         group_channels, offset_scale, remove_center)
+    pitch = offset_mask.shape[-1]
+    rows = offset_mask.numel() // pitch
+    if offset_mask.dim() < 2 or pitch < group * P * 3 or pitch % 2 or rows < input.shape[0] * Ho * Wo:
+        raise RuntimeError(f"offset_mask must hold >= N*Ho*Wo rows of >= G*P*3 (even) elements, got {tuple(offset_mask.shape)}")
+    out = torch.empty((input.shape[0], Ho, Wo, group * group_channels), dtype=input.dtype, device=input.device)
+    with torch.cuda.device(input.device):
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        check(lib.gp_dcnv3_forward_softmax_packed(_vp(input), _vp(offset_mask), _vp(out), pitch, ctypes.byref(d), dt, stream),
+              "dcnv3_forward_packed")
+    return out
+
+
 def dcnv3_backward(input, offset, mask, kernel_h, kernel_w, stride_h, stride_w, pad_h, pad_w, dilation_h, dilation_w,
                    group, group_channels, offset_scale, grad_output, im2col_step, remove_center=0):
     """``DCNv3.dcnv3_backward`` (``src/dcnv3.h:40-59``); note ``grad_output`` sits before ``im2col_step``."""

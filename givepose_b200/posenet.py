@@ -37,7 +37,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import ops
-from .functions import DCNv3Function, dcnv3_forward
+from .functions import DCNv3Function, dcnv3_forward, dcnv3_forward_packed
 
 
 @dataclass
@@ -141,6 +141,7 @@ class DCNv3(nn.Module):
         self._reset_parameters()
         self._cache = {}
         self.fuse_whole_module = True   # first-layer (K = 3) inference path: ops.dcnv3_smallk_fused
+        self.fuse_offset_mask = True    # bf16 inference: offset || mask as one tcgen05 GEMM, rows consumed packed by the sampler
 
     def _reset_parameters(self):   # modules/dcnv3.py:308-316
         for m in (self.offset, self.mask):
@@ -172,8 +173,28 @@ class DCNv3(nn.Module):
         k, s, p, d = self.kernel_size, self.stride, self.pad, self.dilation
         return (k, k, s, s, p, p, d, d, self.group, self.group_channels, self.offset_scale)
 
+    def _offmask_params(self, device):
+        """``offset`` and ``mask`` read the same activation (modules/dcnv3.py:330-334): one [G*P*3 (+ pad to a multiple of 8), C]
+        bf16 weight and one fp32 bias, so both run as ONE tcgen05 GEMM whose rows the sampler consumes in place."""
+        ps = (self.offset.weight, self.offset.bias, self.mask.weight, self.mask.bias)
+        key = (device,) + tuple(p._version for p in ps)
+        if self._cache.get("omkey") != key:
+            with torch.no_grad():
+                n = self.offset.out_features + self.mask.out_features
+                pad = (-n) % 8
+                w = torch.cat([self.offset.weight, self.mask.weight, self.offset.weight.new_zeros(pad, self.channels)])
+                b = torch.cat([self.offset.bias, self.mask.bias, self.offset.bias.new_zeros(pad)])
+                self._cache.update({"omkey": key, "om_w": w.detach().to(torch.bfloat16).contiguous(), "om_b": b.detach().float().contiguous()})
+        return self._cache["om_w"], self._cache["om_b"]
+
     def _sample(self, x, x1):
         """offset / mask-logit Linears on the computed rows, fused-softmax sampler, output projection."""
+        if (self.fuse_offset_mask and _fused(x1) and x1.dtype == torch.bfloat16 and x1.is_cuda and self.channels % 8 == 0
+                and self.group_channels % 4 == 0):
+            w, b = self._offmask_params(x1.device)
+            om = ops.linear_bf16(x1.reshape(-1, self.channels), w, b)        # one launch instead of two cuBLAS GEMMs
+            x = dcnv3_forward_packed(x.contiguous(), om, *self._geom(), 256, self.remove_center)
+            return _lin(x, self.output_proj)
         offset = _lin(x1, self.offset)
         logits = _lin(x1, self.mask)
         x = dcnv3_forward(x.contiguous(), offset.contiguous(), logits.contiguous(), *self._geom(), 256, self.remove_center,
@@ -832,10 +853,15 @@ class PoseNet(nn.Module):
             elif fast_backbone:
                 # fp32 NCHW crops straight into the packed stem: no separate cast / channels_last copies
                 feat = self.backbone(img.float().contiguous(), cdtype)
+            elif self.cfg.precision == "bf16" and not torch.is_grad_enabled():
+                # user-supplied backbone (e.g. the reference's timm ConvNeXt-B, network/backbone.py:36-46): its parameters are
+                # fp32 masters we hold no bf16 copies of, so it runs under autocast; whatever it returns is cast to bf16
+                with torch.autocast("cuda", dtype=torch.bfloat16):
+                    feat = self.backbone(img.float().contiguous(memory_format=torch.channels_last))
+                feat = [f.to(torch.bfloat16) for f in (feat if isinstance(feat, (list, tuple)) else [feat])]
             else:
-                if self.cfg.precision == "bf16" and not torch.is_grad_enabled():
-                    img = img.to(torch.bfloat16)
                 feat = self.backbone(img.contiguous(memory_format=torch.channels_last))
+                feat = list(feat) if isinstance(feat, (list, tuple)) else [feat]
             f_nhwc = feat[0].permute(0, 2, 3, 1)                              # (B, 8, 8, 1024) channel-last view
             if not f_nhwc.is_contiguous():
                 f_nhwc = f_nhwc.contiguous()

@@ -95,8 +95,10 @@ class GradBucket:
 
 
 def surrogate_loss(out: Dict[str, torch.Tensor], target: Dict[str, torch.Tensor]) -> torch.Tensor:
-    """Stand-in for the reference ``PoseLoss`` (``losses/pose_loss.py:30-96``, out of scope this round):
-    L1 on rot / trans / size and smooth-L1 on the two coordinate maps -- every head and the DCNv3 backward get gradients."""
+    """A dataset-free stand-in for the loss (the reference's ``PoseLoss``, ``losses/pose_loss.py:30-96``, is built in
+    ``givepose_b200.loss.PoseLoss`` and is what ``criterion=`` takes; this one needs only prediction-shaped targets, so the
+    step can be exercised without ground-truth point clouds / symmetry labels): L1 on rot / trans / size and smooth-L1 on the
+    two coordinate maps -- every head and the DCNv3 backward get gradients."""
     return (F.l1_loss(out["rot"], target["rot"]) + F.l1_loss(out["trans"], target["trans"]) + F.l1_loss(out["size"], target["size"])
             + F.smooth_l1_loss(out["nocs_coor"], target["nocs_coor"]) + F.smooth_l1_loss(out["ivfc_coor"], target["ivfc_coor"]))
 
@@ -119,9 +121,23 @@ def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: f
     bucket.zero_()   # p.grad are views of the flat buffer: one memset instead of optimizer.zero_grad()
     data = dict(data)
     data.setdefault("roi_mask_deform", data["roi_mask"])
+    n_local = int(data["roi_img"].shape[0])
+    if n_local == 0:
+        raise ValueError("train_step: this rank's RoI shard is empty (batch smaller than the world size); give every rank at "
+                         "least one RoI or drop the rank from the process group")
     out = net(data, device, do_loss=True)
     loss = surrogate_loss(out, target) if criterion is None else sum(criterion(out, target).values())
-    loss.backward()
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        # every loss term is a mean over THIS rank's RoIs and the bucket averages over ranks: weight the rank by
+        # n_local * world / n_global so that unequal shards (shard_range hands the remainder to the low ranks) still give
+        # the single-process full-batch mean gradient of engine/train.py:117-125.  One 4-byte collective, device-side only.
+        cnt = torch.full((1,), float(n_local), dtype=torch.float32, device=loss.device)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+        scaled = loss * (float(n_local * world) / cnt).squeeze(0)
+    else:
+        scaled = loss
+    scaled.backward()
     bucket.allreduce_(group)
     bucket.clip_(clip)
     optimizer.step()
@@ -143,6 +159,23 @@ class GraphedTrainStep:
         dev = torch.device(device)
         self.net, self.optimizer, self.bucket, self.dev = net, optimizer, bucket, dev
         self.clip, self.group, self.criterion = clip, group, criterion
+        # optimizer.step() is INSIDE the graph: everything it reads must live on the device, or the replay silently reuses the
+        # values of capture time.  Adam-family optimizers keep their step counter on the host unless capturable=True; the
+        # learning rate is moved into a device tensor here, so a scheduler (engine/train.py:128 calls scheduler.step() after
+        # every optimizer step; torch's schedulers fill_() a tensor lr in place) or set_lr() takes effect on the next replay.
+        for gidx, g in enumerate(optimizer.param_groups):
+            if "capturable" in g and not g["capturable"]:
+                raise ValueError(f"GraphedTrainStep: {type(optimizer).__name__} must be built with capturable=True (param group "
+                                 f"{gidx}); otherwise use the eager train_step()")
+            if "capturable" not in g and not isinstance(optimizer, torch.optim.SGD):
+                raise ValueError(f"GraphedTrainStep: {type(optimizer).__name__} is not known to be CUDA-graph capturable (host-side "
+                                 "step counters / scalars are baked into the graph); use torch.optim.SGD, a capturable=True "
+                                 "optimizer, or the eager train_step()")
+            if isinstance(g["lr"], torch.Tensor):
+                if g["lr"].device != dev:
+                    g["lr"] = g["lr"].to(dev)
+            else:
+                g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
         self.data = {k: v.to(dev).clone() for k, v in example_data.items()}
         self.target = {k: v.to(dev).clone() for k, v in example_target.items()}
         side = torch.cuda.Stream(dev)
@@ -156,6 +189,12 @@ class GraphedTrainStep:
         # thread_local: the NCCL watchdog thread polls events while we capture
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.loss = train_step(net, self.data, self.target, optimizer, bucket, dev, clip, group, criterion)
+
+    def set_lr(self, lr: float, group: int | None = None) -> None:
+        """Change the learning rate seen by the NEXT replay (in-place fill of the device tensor the captured step reads)."""
+        for gidx, g in enumerate(self.optimizer.param_groups):
+            if group is None or gidx == group:
+                g["lr"].fill_(float(lr))
 
     def __call__(self, data=None, target=None) -> torch.Tensor:
         """Refresh the static buffers (skipped for ``None`` / for tensors that already ARE the static buffers) and replay."""

@@ -83,6 +83,14 @@ int gp_dcnv3_forward(const void *input, const void *offset, const void *mask, vo
 int gp_dcnv3_forward_softmax(const void *input, const void *offset, const void *mask_logits, void *out,
                              const gp_dcnv3_desc *desc, int dtype, void *stream);
 
+/* As gp_dcnv3_forward_softmax, but offsets and mask logits come PACKED as the output rows of ONE fused Linear
+ * (modules/dcnv3.py:330-334: `offset` and `mask` read the same activation): row q of `offset_mask` holds
+ * [G*P*2 offsets | G*P mask logits | padding] and rows are `pitch` elements apart (pitch >= G*P*3 and even;
+ * 16-byte aligned base).  Tiled kernels only: GP_ERR_UNSUPPORTED where gp_dcnv3_forward would take its
+ * generic kernel (odd gc, fp64). */
+int gp_dcnv3_forward_softmax_packed(const void *input, const void *offset_mask, void *out, long long pitch,
+                                    const gp_dcnv3_desc *desc, int dtype, void *stream);
+
 /* bytes of scratch gp_dcnv3_backward needs (0 for F32/F64: grads accumulate in place; for BF16/F16 an
  * fp32 image of grad_input, as the reference does for half, dcnv3_cuda.cu:126-133,168-173). */
 size_t gp_dcnv3_backward_workspace(const gp_dcnv3_desc *desc, int dtype);
@@ -266,10 +274,12 @@ int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);
 
 /* Further kernel-selection knobs (tuning sweeps and A/B measurements only; results never depend on them beyond
  * floating-point summation order).  Returns GP_ERR_SHAPE for an unknown key / value.
- *   GP_OPT_BWD_MODE      0 = one-pass scatter backward (one 16-byte reduction per lane per corner, round-1 kernel)
- *                        1 = split backward (default): grad_offset/grad_mask kernel + grad_input with in-SM
- *                            pre-aggregation (dcnv3_gin_binned: counting sort by footprint cell, register accumulation,
- *                            one reduction per destination line of the tile's window)
+ *   GP_OPT_BWD_MODE      0 = one-pass scatter backward (default): one 16-byte reduction per lane per corner
+ *                        1 = split backward: grad_offset/grad_mask kernel + grad_input with in-SM pre-aggregation
+ *                            (dcnv3_gin_binned: counting sort by footprint cell, register accumulation, one reduction per
+ *                            destination line of the tile's window: 7.6x fewer reduction sectors, but the sort + gather
+ *                            costs more SM issue slots than the reductions cost L2 bandwidth -- measured 1.86 ms against
+ *                            1.38 ms at BASELINE config 2, profiles/r02a_sweep_bwd_split_vs_scatter.json)
  *   GP_OPT_GIN_TILE_H/W  output tile of the binned grad_input kernel (powers of two, default 8 x 8)
  *   GP_OPT_GIN_THREADS   its CTA size: 128, 192 (default) or 256
  *   GP_OPT_FWD_MODE      0 = round-1 forward kernel, 1 = packed-record forward (default) */

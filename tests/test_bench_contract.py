@@ -20,9 +20,15 @@ def test_reference_arm_prints_the_contract_line():
     line = json.loads(r.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["metric"] == "dcnv3_fwd_bwd_algorithmic_GBps" and line["unit"] == "GB/s"
     assert line["higher_is_better"] is True and line["value"] > 0 and line["gpu_launches"] == 0
-    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    from baseline import reference as R
+    # the reference's own dcnv3_func.py when it is staged (baseline/_ref, written by build()) or present; the oracle port otherwise
+    assert line["cpu_baseline"]["kind"] == ("reference" if R.root() else "port")
+    assert line["cpu_baseline"]["cores"] >= 1 and "N=64" in line["cpu_baseline"]["sample"]
     assert line["e2e"] == {"value": line["value"], "unit": "GB/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in line["config"]
+    assert line["steps"] == 1 and "workload" in line["config"]
+    sys.path.insert(0, ROOT)
+    import bench
+    assert line["config"] == bench.bench_config(1, "T")        # the SAME config our arm prints (same_config in the driver's ratio)
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -384,3 +384,45 @@ def test_backward_elementwise_with_absolute_floor(ops, O, bwd_options):
                 tol = 1e-4 * r_.abs() + 1e-5 * r_.abs().max()
                 bad = (d > tol)
                 assert bad.float().mean().item() < (1e-5 if nm != "grad_input" else 1e-6), (dist, mode, nm, bad.sum().item())
+
+
+def test_full_size_bf16_vs_c_oracle_sampled_images(ops, O, full_size):
+    """BASELINE config 2 in bf16 (N = 64, the size bench.py --dtype bf16 times), forward + backward, C oracle (fp32 arithmetic
+    on the same bf16-rounded inputs) on a strided subset of the images; indices / bounds stay bit-exact."""
+    inp, off, m, gout, args = (t.to(torch.bfloat16) if torch.is_tensor(t) else t for t in full_size)
+    out = ops.dcnv3_forward(inp, off, m, *args, 256, 0)
+    gi, go, gm = ops.dcnv3_backward(inp, off, m, *args, gout, 256, 0)
+    assert out.dtype == torch.bfloat16 and gi.dtype == torch.bfloat16
+    sel = [0, 21, 42, 63]
+    ci, co, cm, cg = (t[sel].float().cpu().contiguous() for t in (inp, off, m, gout))
+    assert _rel(out[sel], O.forward(ci, co, cm, *args, 0)) < BF16_TOL
+    rgi, rgo, rgm = O.backward(ci, co, cm, cg, *args, 0)
+    assert _rel(gi[sel], rgi) < BF16_TOL and _rel(go[sel], rgo) < BF16_TOL and _rel(gm[sel], rgm) < BF16_TOL
+    hw_o, fl_o = O.index(co, len(sel), 64, 64, *args[:8], 8, 1.0, 0)
+    hw_g, fl_g = ops.dcnv3_sample_index(off[sel].contiguous(), len(sel), 64, 64, *args[:8], 8, 1.0, 0)
+    assert torch.equal(hw_g.cpu(), hw_o) and torch.equal(fl_g.cpu(), fl_o)
+
+
+def test_forward_inf_next_to_the_border_documented_deviation(ops, O):
+    """for a footprint corner OUTSIDE the image the forward reads a pixel of the same footprint that lies
+    inside, with weight 0.  For finite inputs that is exactly the reference's "outside counts as 0" (cuh:55-75); an Inf in that
+    borrowed pixel gives 0 * Inf = NaN where the reference keeps the value it computes without it.  This test pins both
+    halves: finite inputs agree everywhere; with Inf border pixels every output the reference keeps finite is either equal
+    or NaN here (never a different finite number), and outputs that do not touch the border are untouched."""
+    gen = torch.Generator().manual_seed(17)
+    N, H, W, G, gc = 1, 12, 12, 2, 16
+    inp = torch.randn(N, H, W, G * gc, generator=gen)
+    off = (torch.rand(N, H, W, G * 18, generator=gen) - 0.5) * 3
+    m = torch.softmax(torch.randn(N, H, W, G, 9, generator=gen), -1).reshape(N, H, W, G * 9)
+    args = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    assert _rel(ops.dcnv3_forward(inp.cuda(), off.cuda(), m.cuda(), *args, 256, 0), O.forward(inp, off, m, *args, 0)) < 1e-5
+    bad = inp.clone()
+    bad[:, 0, :, :] = float("inf")            # the whole first image row
+    ref = O.forward(bad, off, m, *args, 0)
+    got = ops.dcnv3_forward(bad.cuda(), off.cuda(), m.cuda(), *args, 256, 0).cpu()
+    fin = torch.isfinite(ref)
+    same = torch.isclose(got, ref, rtol=1e-5, atol=1e-6)
+    assert (same | torch.isnan(got))[fin].all()            # never a different finite number
+    assert (~torch.isfinite(got[~fin])).all()              # where the reference overflows, so do we
+    # rows far from the poisoned border (no footprint can reach image row 0 with |offset| < 1.5 + kernel reach 1) are exact
+    assert torch.isfinite(got[:, 5:]).all() and _rel(got[:, 5:], ref[:, 5:]) < 1e-5

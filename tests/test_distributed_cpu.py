@@ -96,3 +96,55 @@ def test_bucket_clip_equals_clip_grad_norm():
         assert torch.allclose(n, n_ref, rtol=1e-6)
         for a, b in zip(net.parameters(), ref.parameters()):
             assert torch.allclose(a.grad, b.grad, rtol=1e-5, atol=1e-8)
+
+
+class _TinyNet(torch.nn.Module):
+    """PoseNet-shaped call signature (data dict, device, do_loss) around one Linear: enough for train_step's host logic."""
+
+    def __init__(self):
+        super().__init__()
+        self.lin = torch.nn.Linear(6, 3)
+
+    def forward(self, data, device, do_loss=False, pred_scale=None):
+        return {"y": self.lin(data["roi_img"])}
+
+
+def _crit(out, target):
+    return {"l2": (out["y"] - target["y"]).square().mean()}   # a mean over the rank's RoIs, like every PoseLoss term
+
+
+def _worker_unequal(rank, world, port, out):
+    from givepose_b200.train import train_step
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        net, ref = _TinyNet(), _TinyNet()
+        ref.load_state_dict(net.state_dict())
+        B = 5                                                   # shards of 3 and 2 RoIs
+        x, y = torch.randn(B, 6), torch.randn(B, 3)
+        lo, hi = shard_range(B, rank, world)
+        bucket = GradBucket(net.parameters())
+        opt = torch.optim.SGD(net.parameters(), lr=0.0)
+        train_step(net, {"roi_img": x[lo:hi], "roi_mask": x[lo:hi]}, {"y": y[lo:hi]}, opt, bucket, "cpu", clip=1e9, criterion=_crit)
+        _crit(ref({"roi_img": x}, "cpu"), {"y": y})["l2"].backward()      # the single-process full-batch step (engine/train.py:117-125)
+        want = torch.cat([p.grad.flatten() for p in ref.parameters()])
+        ok = torch.allclose(bucket.flat, want, atol=1e-6)
+        empty = False
+        try:
+            train_step(net, {"roi_img": x[:0], "roi_mask": x[:0]}, {"y": y[:0]}, opt, bucket, "cpu", criterion=_crit)
+        except ValueError:
+            empty = True
+        out[rank] = (ok, empty)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_unequal_shards_give_the_full_batch_mean_gradient_gloo_world2():
+    """shard_range hands the remainder to the low ranks; train_step weights each rank by n_local*world/n_global so the
+    averaged gradient equals the single-process full-batch mean (and refuses an empty shard before any collective)."""
+    world, port = 2, _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker_unequal, args=(world, port, out), nprocs=world, join=True)
+        assert dict(out) == {0: (True, True), 1: (True, True)}

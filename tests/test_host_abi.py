@@ -58,9 +58,9 @@ def test_dropin_module_and_distribution():
 
 
 def test_product_never_imports_oracle():
-    """The oracle is test infrastructure: nothing under givepose_b200/ may reference it."""
+    """The oracle and the reference-arm plumbing are test infrastructure: nothing under givepose_b200/ may reference them."""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "givepose_b200")):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
-                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
+                assert not re.search(r"^\s*(from|import)\s+(oracle|baseline)\b", src, flags=re.M), os.path.join(dirpath, f)

@@ -12,6 +12,8 @@
 //   mode 2  16-bit rows, 4 lanes x 16 B per corner (half a line per gather, 8 units per warp request)
 //   mode 3  mode 0 without the record reads (offsets derived from a per-unit seed in registers: pure gather + store)
 //   mode 4  shared-memory reads only: the LDS patterns the kernels use (16-byte broadcast records, 128-byte rows)
+//   mode 5  the backward's scatter alone: 36 red.global.add.v4.f32 line reductions per unit to the same addresses (fp32)
+//   mode 6  gather + scatter: 36 line gathers AND 36 line reductions per unit (the one-pass backward's memory pattern)
 // Output: ms per launch, units/clk/SM, and for modes 0-3 the bytes-gathered rate.  The forward can not be faster than
 // mode 0 (fp32) / mode 1-2 (bf16) with the same decomposition; the figure bench.py quotes as `l1_gather_floor_ms`.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/gather_rates tools/micro/gather_rates.cu
@@ -47,11 +49,15 @@ __global__ void make_offsets(int *__restrict__ offs, int dist) {
     }
 }
 
+__device__ __forceinline__ void red_v4(float *a, float x, float y, float z, float w) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(a), "f"(x), "f"(y), "f"(z), "f"(w) : "memory");
+}
+
 template <int MODE>
 __global__ void __launch_bounds__(256, 4)
 gather(const void *__restrict__ in, const int *__restrict__ offs, void *__restrict__ out) {
     constexpr int L = MODE == 2 ? 4 : 8;            // lanes per unit
-    constexpr int EB = MODE == 0 || MODE == 3 ? 4 : 2;   // element bytes
+    constexpr int EB = MODE == 1 || MODE == 2 ? 2 : 4;   // element bytes
     constexpr int LB = GC * EB / L;                 // bytes per lane per corner: 16, 8, 16
     constexpr int UPB = 256 / L;
     // tile decode as dcnv3_fwd_tile: gch fastest, then tile x, tile y, image
@@ -84,7 +90,11 @@ gather(const void *__restrict__ in, const int *__restrict__ offs, void *__restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const char *ptr = in_g + (long long)oo[k] * (C * EB);
-                if (LB == 16) {
+                if (MODE == 5 || MODE == 6) {   // `out` is the fp32 accumulation image (same shape as `in`)
+                    float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+                    if (MODE == 6) v = __ldg(reinterpret_cast<const float4 *>(ptr));
+                    red_v4(reinterpret_cast<float *>((char *)out + (ptr - (const char *)in)), v.x, v.y, v.z, v.w);
+                } else if (LB == 16) {
                     const float4 v = __ldg(reinterpret_cast<const float4 *>(ptr));
                     acc[0] += v.x; acc[1] += v.y; acc[2] += v.z; acc[3] += v.w;
                 } else {
@@ -94,6 +104,7 @@ gather(const void *__restrict__ in, const int *__restrict__ offs, void *__restri
             }
         }
         char *o_ptr = (char *)out + (q * C + g * GC) * EB + cl * LB;
+        if (MODE == 5 || MODE == 6) continue;
         if (LB == 16) *reinterpret_cast<float4 *>(o_ptr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         else *reinterpret_cast<float2 *>(o_ptr) = make_float2(acc[0], acc[1]);
     }
@@ -137,7 +148,7 @@ template <int MODE> void run(const char *name, const void *in, const int *offs, 
     cudaError_t e = cudaGetLastError();
     float ms = 0; cudaEventElapsedTime(&ms, a, b); ms /= reps;
     const double units = (double)N * H * W * G;
-    const int eb = (MODE == 0 || MODE == 3) ? 4 : 2;
+    const int eb = (MODE == 1 || MODE == 2) ? 2 : 4;
     printf("gather mode %d dist %c %-44s %7.4f ms  %6.2f clk/unit/SM @1.965GHz  gathered %6.0f GB/s  %s\n", MODE, dist ? 'M' : 'T', name,
            ms, ms * 1e-3 * 1.965e9 / (units / 148), units * 36 * GC * eb / ms / 1e6, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
@@ -168,6 +179,8 @@ int main() {
         run<0>("fp32, 8 lanes x 16 B (full lines)", in, offs, out, dist);
         run<1>("16-bit, 8 lanes x 8 B (half lines)", in, offs, out, dist);
         run<2>("16-bit, 4 lanes x 16 B (half lines)", in, offs, out, dist);
+        run<5>("fp32 scatter only: 36 red.v4 lines per unit", in, offs, out, dist);
+        run<6>("fp32 gather + scatter: 36 + 36 lines per unit", in, offs, out, dist);
     }
     run<3>("fp32, offsets from registers (no record reads)", in, offs, out, 0);
     run_lds<0>("LDS.128, 4 distinct 16 B records per warp (8-lane broadcast)", sink);
