@@ -480,11 +480,11 @@ def run_posenet(args, rank, world, dev, dist):
         e1.record()
         barrier()
         t_eager = torch.tensor([e0.elapsed_time(e1) / 3], device=dev, dtype=torch.float64)
-        # the same step captured once as a CUDA graph (zero -> fwd -> loss -> bwd -> all-reduce -> clip -> SGD) and replayed
+        # the same step with zero -> fwd -> loss -> bwd -> all-reduce -> clip captured once as a CUDA graph and replayed; SGD steps eagerly
         from givepose_b200 import _lib
         from givepose_b200.train import GraphedTrainStep
         n0 = int(_lib.lib.gp_launch_count())
-        mode = "one CUDA graph per step (givepose_b200.train.GraphedTrainStep)"
+        mode = "one CUDA graph per step (zero -> fwd -> loss -> bwd -> all-reduce -> clip) + eager optimizer.step() (givepose_b200.train.GraphedTrainStep)"
         try:
             gstep = GraphedTrainStep(net, opt, bucket, dev, tdata, tgt, criterion=crit, warmup=1)
             ours_per_step = (int(_lib.lib.gp_launch_count()) - n0) // 2   # 1 warm-up + the captured step

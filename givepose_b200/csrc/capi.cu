@@ -8,6 +8,7 @@
 
 #include "dcnv3_kernels.cuh"
 #include "dcnv3_gin_binned.cuh"
+#include "dcnv3_bwd_fused.cuh"
 
 namespace gp {
 unsigned long long g_launches = 0;
@@ -16,7 +17,7 @@ struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 2;   // measured best on B200 (profiles/r01_sweep.md)
     int vec16 = 8;   // forward: channels per lane for 16-bit storage (8 = 16-byte requests, 4 = 8-byte requests)
                      // backward always uses 4: its fp32 reductions then cover whole 128-byte lines per request
-    int bwd_mode = 0;              // 0: one-pass scatter kernel (fastest measured, profiles/r02a_*); 1: grad_offset/grad_mask kernel + binned grad_input kernel
+    int bwd_mode = 0;              // 0: one-pass scatter kernel (fastest measured, profiles/r02_it1_*); 1: grad_offset/grad_mask kernel + binned grad_input kernel
     int gin_th = 8, gin_tw = 8;    // output tile of the binned grad_input kernel
     int gin_nt = 192;              // its CTA size
     int fwd_mode = 1;
@@ -31,7 +32,7 @@ static void init_tuning() {
     if (const char *e = getenv("GP_TILE_W")) g_tune.tile_w = atoi(e);
     if (const char *e = getenv("GP_GS")) g_tune.gs = atoi(e);
     if (const char *e = getenv("GP_VEC16")) g_tune.vec16 = atoi(e) == 4 ? 4 : 8;
-    if (const char *e = getenv("GP_BWD_MODE")) g_tune.bwd_mode = atoi(e) ? 1 : 0;
+    if (const char *e = getenv("GP_BWD_MODE")) { const int v = atoi(e); g_tune.bwd_mode = v >= 0 && v <= 2 ? v : 0; }
     if (const char *e = getenv("GP_FWD_MODE")) g_tune.fwd_mode = atoi(e) ? 1 : 0;
 }
 
@@ -226,6 +227,64 @@ static cudaError_t launch_gin_binned(const void *off, const void *msk, const voi
     return cudaErrorInvalidValue;
 }
 
+// ---- fused backward with in-SM pre-aggregation (dcnv3_bwd_fused.cuh) --------------------------------------------------
+static bool plan_bwd_fused(const KParams &p, int dtype, KParams &pf, int *L_out) {
+    if (dtype == GP_F64 || p.gc % 4) return false;
+    const int L = p.gc / 4;
+    if (L > 32 || (L & (L - 1))) return false;
+    if (p.H > 32767 || p.W > 32767) return false;
+    if ((long long)p.H * p.W * p.C * 4 >= (1ll << 31)) return false;
+    init_tuning();
+    auto pow2_floor = [](int v) { int r = 1; while (r * 2 <= v) r *= 2; return r; };
+    auto lg2 = [](int v) { int r = 0; while ((1 << r) < v) ++r; return r; };
+    int th = pow2_floor(g_tune.gin_th < 1 ? 1 : g_tune.gin_th), tw = pow2_floor(g_tune.gin_tw < 1 ? 1 : g_tune.gin_tw);
+    while (th * tw * p.P > kFusedThreads * kFusedSPT || th * tw > 256) {
+        if (th >= tw && th > 1) th /= 2; else if (tw > 1) tw /= 2; else return false;
+    }
+    pf = p;
+    pf.tile_h = th; pf.tile_w = tw; pf.gs = 1; pf.gchunks = p.G;
+    pf.lg_tw = lg2(tw); pf.lg_tp = lg2(th * tw); pf.lg_gs = 0;
+    pf.tiles_y = (p.Ho + th - 1) / th;
+    pf.tiles_x = (p.Wo + tw - 1) / tw;
+    if ((long long)p.N * pf.tiles_y * pf.tiles_x * pf.gchunks >= (1ll << 31)) return false;
+    if (bwd_fused_smem(th * tw, p.P, L) > 160 * 1024) return false;
+    *L_out = L;
+    return true;
+}
+
+template <typename T, int L>
+static cudaError_t launch_bwd_fused_one(const void *in, const void *off, const void *msk, const void *gout, float *gin,
+                                        void *goff, void *gmsk, const KParams &pf, cudaStream_t st) {
+    const size_t sm = bwd_fused_smem(pf.tile_h * pf.tile_w, pf.P, L);
+    const unsigned grid = tile_grid(pf);
+    cudaError_t e = cudaSuccess;
+    if (pf.P == 9) {
+        auto k = dcnv3_bwd_fused<T, L, true, 6>;
+        if (sm > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) k<<<grid, kFusedThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, (const T *)gout, gin, (T *)goff, (T *)gmsk, pf);
+    } else {
+        auto k = dcnv3_bwd_fused<T, L, false, 6>;
+        if (sm > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+        if (e == cudaSuccess) k<<<grid, kFusedThreads, sm, st>>>((const T *)in, (const T *)off, (const T *)msk, (const T *)gout, gin, (T *)goff, (T *)gmsk, pf);
+    }
+    count_launch();
+    return e;
+}
+
+template <typename T>
+static cudaError_t launch_bwd_fused(const void *in, const void *off, const void *msk, const void *gout, float *gin, void *goff,
+                                    void *gmsk, const KParams &pf, int L, cudaStream_t st) {
+    switch (L) {
+        case 1: return launch_bwd_fused_one<T, 1>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+        case 2: return launch_bwd_fused_one<T, 2>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+        case 4: return launch_bwd_fused_one<T, 4>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+        case 8: return launch_bwd_fused_one<T, 8>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+        case 16: return launch_bwd_fused_one<T, 16>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+        case 32: return launch_bwd_fused_one<T, 32>(in, off, msk, gout, gin, goff, gmsk, pf, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
 template <typename T, bool SOFTMAX>
 static void launch_fwd_generic(const void *in, const void *off, const void *msk, void *out, const KParams &p,
                                cudaStream_t st) {
@@ -319,7 +378,7 @@ int gp_set_tuning(int tile_h, int tile_w, int gs, int vec16) {
 int gp_set_option(int key, int value) {
     init_tuning();
     switch (key) {
-        case GP_OPT_BWD_MODE: if (value != 0 && value != 1) return GP_ERR_SHAPE; g_tune.bwd_mode = value; return GP_OK;
+        case GP_OPT_BWD_MODE: if (value < 0 || value > 2) return GP_ERR_SHAPE; g_tune.bwd_mode = value; return GP_OK;
         case GP_OPT_GIN_TILE_H: if (value < 1) return GP_ERR_SHAPE; g_tune.gin_th = value; return GP_OK;
         case GP_OPT_GIN_TILE_W: if (value < 1) return GP_ERR_SHAPE; g_tune.gin_tw = value; return GP_OK;
         case GP_OPT_GIN_THREADS: if (value != 128 && value != 192 && value != 256) return GP_ERR_SHAPE; g_tune.gin_nt = value; return GP_OK;
@@ -399,6 +458,13 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
     int L = 0, vec = 0, Lg = 0, nt = 0;
     KParams pg;
     init_tuning();
+    if (g_tune.bwd_mode == 2 && plan_bwd_fused(p, dtype, pg, &Lg)) {
+        // one kernel: in-SM aggregated grad_input (sort + row walk) and the grad_offset / grad_mask gathers
+        if (dtype == GP_F32) ce = launch_bwd_fused<float>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, pg, Lg, st);
+        else if (dtype == GP_BF16) ce = launch_bwd_fused<__nv_bfloat16>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, pg, Lg, st);
+        else ce = launch_bwd_fused<__half>(input, offset, mask, grad_out, (float *)acc, grad_offset, grad_mask, pg, Lg, st);
+        if (ce != cudaSuccess) return (int)ce;
+    } else {
     const bool split = g_tune.bwd_mode == 1 && plan_gin_binned(p, dtype, pg, &Lg, &nt);
     if (plan_tiled(p, dtype, &L, &vec, !split)) {
         if (split) {
@@ -426,6 +492,7 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
             case GP_F16: launch_bwd_generic<__half>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
             case GP_F64: launch_bwd_generic<double>(input, offset, mask, grad_out, acc, grad_offset, grad_mask, p, st); break;
         }
+    }
     }
     ce = cudaGetLastError();
     if (ce != cudaSuccess) return (int)ce;

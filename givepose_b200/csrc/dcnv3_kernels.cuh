@@ -9,13 +9,16 @@
 //   CTA       = a tile_h x tile_w patch of output pixels x `gs` groups of ONE image, so the input rows it
 //               gathers form a compact window that stays in L1 (channel-last rows of one group are
 //               contiguous: gc*sizeof(T) bytes = one 128-byte line for gc=32 fp32).
-//   records   = the CTA's offset / mask rows are read once, coalesced; ONE thread per (unit, point) turns
-//               them into a 24-byte sampling record in shared memory (corner-1 element offset, bounds
-//               flags, and either the four mask-folded bilinear weights (forward) or lh/lw/mask (backward);
-//               for the fused variant the softmax over the P points happens here).  The sampling loop reads
-//               a record with two conflict-free broadcast LDS and does no coordinate arithmetic at all:
-//               the kernels are bound by L1 wavefronts (one 128-byte line per corner per unit), so the
-//               instruction stream has to stay well under 4 issue slots per wavefront.
+//   records   = ONE thread per unit reads the unit's offset / mask row (P (x, y) pairs + P mask values, straight from global
+//               memory with read-only loads: a 72-byte stride between the threads of a warp) and turns its P points into
+//               24-byte sampling records in shared memory: byte offset of the footprint + bounds flags, and either the
+//               four mask-folded bilinear weights (forward) or lh / lw / mask (backward); unit-level arithmetic (pixel
+//               decode, p0, the softmax of the fused variant) is done once per unit, kernel indices are compile-time for
+//               3x3.  (An earlier one-thread-per-(unit, point) builder with coalesced row reads spent 35 % of the kernel's
+//               instructions; staging the rows through shared memory was measured and dropped)  The
+//               sampling loop reads a record with two broadcast LDS and does no coordinate arithmetic at all: the kernels
+//               are bound by L1 wavefronts (one 128-byte line per corner per unit), so the instruction stream has to stay
+//               well under 4 issue slots per wavefront.
 //   thread    = VEC channels of one unit; L = gc/VEC consecutive lanes form a unit, so every corner
 //               gather of a unit is one fully-used coalesced request.
 //   backward  = same tiling; grad_input goes out as 16-byte vector reductions (REDG.ADD.F32x4) that
@@ -139,7 +142,8 @@ __device__ __forceinline__ void build_records(const T *__restrict__ off, const T
                 if (sp.flags & F_IN) {
                     bf.x = (sp.h_low * WC + sp.w_low * C) * (int)sizeof(T);
                     bf.y = (int)(sp.flags | ((sp.flags & 30u) == 30u ? F_ALL : 0u));
-                    w = make_float4(sp.lh, sp.lw, m, 0.f);
+                    // spare word: the footprint cell (h_low + 1, w_low + 1), read by the in-SM aggregation of dcnv3_bwd_fused
+                    w = make_float4(sp.lh, sp.lw, m, __int_as_float(((sp.h_low + 1) << 16) | (sp.w_low + 1)));
                 }
                 if (!(bf.y & (int)F_ALL)) interior = 0u;
             } else if (sp.flags & F_IN) {

@@ -111,12 +111,10 @@ def make_targets(B: int, device, seed: int = 0) -> Dict[str, torch.Tensor]:
                                          "nocs_coor": r(B, 3, 64, 64) * 0.3, "ivfc_coor": r(B, 3, 64, 64) * 0.3}.items()}
 
 
-def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: float = 5.0, group=None, criterion=None) -> float:
-    """One data-parallel step on this rank's shard: forward (autograd path: torch CUDA ops around ``DCNv3Function``) ->
-    loss -> backward (DCNv3 backward kernel) -> gradient all-reduce -> clip (``engine/train.py:126``) -> step.
-
-    ``criterion``: a ``givepose_b200.loss.PoseLoss`` -- then ``target`` is the ground-truth dict of the reference's data
-    loader and the loss is the sum of its terms as in ``engine/train.py:120-122``; ``None`` keeps the simple surrogate."""
+def forward_backward(net, data, target, bucket: GradBucket, device, clip: float = 5.0, group=None, criterion=None):
+    """Everything of a data-parallel step up to (not including) the optimizer: zero the bucket -> forward (autograd path: torch
+    CUDA ops around ``DCNv3Function``) -> loss -> backward (DCNv3 backward kernel) -> gradient all-reduce -> clip
+    (``engine/train.py:126``).  Device-side only (no host sync), which is what ``GraphedTrainStep`` captures."""
     net.train()
     bucket.zero_()   # p.grad are views of the flat buffer: one memset instead of optimizer.zero_grad()
     data = dict(data)
@@ -140,16 +138,33 @@ def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: f
     scaled.backward()
     bucket.allreduce_(group)
     bucket.clip_(clip)
-    optimizer.step()
     return loss.detach()
 
 
+def train_step(net, data, target, optimizer, bucket: GradBucket, device, clip: float = 5.0, group=None, criterion=None) -> float:
+    """One data-parallel step on this rank's shard: ``forward_backward`` (forward -> loss -> backward -> all-reduce -> clip)
+    then ``optimizer.step()``.
+
+    ``criterion``: a ``givepose_b200.loss.PoseLoss`` -- then ``target`` is the ground-truth dict of the reference's data
+    loader and the loss is the sum of its terms as in ``engine/train.py:120-122``; ``None`` keeps the simple surrogate."""
+    loss = forward_backward(net, data, target, bucket, device, clip, group, criterion)
+    optimizer.step()
+    return loss
+
+
 class GraphedTrainStep:
-    """``train_step`` captured ONCE as a CUDA graph and replayed: zero grads -> forward -> loss -> backward (DCNv3 backward
-    kernel) -> NCCL all-reduce of the flat bucket -> clip -> optimizer step are ~4400 launches for 48 RoIs, i.e. the eager
-    step is bound by launch overhead, not by the GPU.  Inputs and targets live in static device buffers that ``__call__``
-    refreshes (H2D or D2D copies on the same stream, ahead of the replay).  Nothing on the path synchronises with the host
-    (``PoseLoss`` selects the symmetric rotations on device), which is what makes the capture legal.
+    """``forward_backward`` captured ONCE as a CUDA graph and replayed, followed by an EAGER ``optimizer.step()``: zero grads ->
+    forward -> loss -> backward (DCNv3 backward kernel) -> NCCL all-reduce of the flat bucket -> clip are ~4400 launches for
+    48 RoIs, i.e. the eager step is bound by launch overhead, not by the GPU.  Inputs and targets live in static device
+    buffers that ``__call__`` refreshes (H2D or D2D copies on the same stream, ahead of the replay).  Nothing in the captured
+    part synchronises with the host (``PoseLoss`` selects the symmetric rotations on device), which makes the capture legal.
+
+    The optimizer step stays OUTSIDE the graph on purpose: a captured step bakes every host-side scalar it reads -- the
+    learning rate, Adam's step counter -- into the graph, so a scheduler (``engine/train.py:128`` calls ``scheduler.step()``
+    after every optimizer step) or a non-capturable optimizer (the reference's default Ranger, Adam / AdamW without
+    ``capturable=True``) would be silently ignored on replay, and torch's SGD reads a tensor learning rate through ``.item()``
+    (a sync) outside ``torch.compile``.  Eagerly it is a handful of multi-tensor launches on the gradients the graph left in
+    ``bucket`` (``p.grad`` are views of it), works with any optimizer and any scheduler, and costs ~0.1 ms.
 
     The ``warmup`` eager steps before the capture are real optimisation steps on ``example_data`` (cuDNN algorithm
     selection, momentum buffers, the NCCL communicator all have to exist before capture)."""
@@ -159,23 +174,6 @@ class GraphedTrainStep:
         dev = torch.device(device)
         self.net, self.optimizer, self.bucket, self.dev = net, optimizer, bucket, dev
         self.clip, self.group, self.criterion = clip, group, criterion
-        # optimizer.step() is INSIDE the graph: everything it reads must live on the device, or the replay silently reuses the
-        # values of capture time.  Adam-family optimizers keep their step counter on the host unless capturable=True; the
-        # learning rate is moved into a device tensor here, so a scheduler (engine/train.py:128 calls scheduler.step() after
-        # every optimizer step; torch's schedulers fill_() a tensor lr in place) or set_lr() takes effect on the next replay.
-        for gidx, g in enumerate(optimizer.param_groups):
-            if "capturable" in g and not g["capturable"]:
-                raise ValueError(f"GraphedTrainStep: {type(optimizer).__name__} must be built with capturable=True (param group "
-                                 f"{gidx}); otherwise use the eager train_step()")
-            if "capturable" not in g and not isinstance(optimizer, torch.optim.SGD):
-                raise ValueError(f"GraphedTrainStep: {type(optimizer).__name__} is not known to be CUDA-graph capturable (host-side "
-                                 "step counters / scalars are baked into the graph); use torch.optim.SGD, a capturable=True "
-                                 "optimizer, or the eager train_step()")
-            if isinstance(g["lr"], torch.Tensor):
-                if g["lr"].device != dev:
-                    g["lr"] = g["lr"].to(dev)
-            else:
-                g["lr"] = torch.tensor(float(g["lr"]), dtype=torch.float32, device=dev)
         self.data = {k: v.to(dev).clone() for k, v in example_data.items()}
         self.target = {k: v.to(dev).clone() for k, v in example_target.items()}
         side = torch.cuda.Stream(dev)
@@ -188,20 +186,16 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         # thread_local: the NCCL watchdog thread polls events while we capture
         with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
-            self.loss = train_step(net, self.data, self.target, optimizer, bucket, dev, clip, group, criterion)
-
-    def set_lr(self, lr: float, group: int | None = None) -> None:
-        """Change the learning rate seen by the NEXT replay (in-place fill of the device tensor the captured step reads)."""
-        for gidx, g in enumerate(self.optimizer.param_groups):
-            if group is None or gidx == group:
-                g["lr"].fill_(float(lr))
+            self.loss = forward_backward(net, self.data, self.target, bucket, dev, clip, group, criterion)
 
     def __call__(self, data=None, target=None) -> torch.Tensor:
-        """Refresh the static buffers (skipped for ``None`` / for tensors that already ARE the static buffers) and replay."""
+        """Refresh the static buffers (skipped for ``None`` / for tensors that already ARE the static buffers), replay the
+        captured forward/backward/all-reduce/clip, then step the optimizer eagerly (current learning rate, any optimizer)."""
         for static, new in ((self.data, data), (self.target, target)):
             if new is not None:
                 for k, v in new.items():
                     if v is not static[k]:
                         static[k].copy_(v, non_blocking=True)
         self.graph.replay()
+        self.optimizer.step()
         return self.loss

@@ -279,7 +279,10 @@ int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);
  *                            (dcnv3_gin_binned: counting sort by footprint cell, register accumulation, one reduction per
  *                            destination line of the tile's window: 7.6x fewer reduction sectors, but the sort + gather
  *                            costs more SM issue slots than the reductions cost L2 bandwidth -- measured 1.86 ms against
- *                            1.38 ms at BASELINE config 2, profiles/r02a_sweep_bwd_split_vs_scatter.json)
+ *                            1.38 ms at BASELINE config 2, profiles/r02_it1_sweep_bwd_split_vs_scatter.json)
+ *                        2 = ONE kernel (dcnv3_bwd_fused): the same gathers, and grad_input aggregated inside the SM by a
+ *                            counting sort of the CTA's samples by footprint cell + a register row walk (each sample
+ *                            visited once, ~3x fewer reductions), so the two phases overlap across the CTAs of an SM
  *   GP_OPT_GIN_TILE_H/W  output tile of the binned grad_input kernel (powers of two, default 8 x 8)
  *   GP_OPT_GIN_THREADS   its CTA size: 128, 192 (default) or 256
  *   GP_OPT_FWD_MODE      0 = round-1 forward kernel, 1 = packed-record forward (default) */

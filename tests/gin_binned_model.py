@@ -9,9 +9,12 @@ CELLS, WIN_W = 1024, 32   # kGinCells, kGinWinW
 
 
 def grad_input_binned(off, msk, gout, N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh, dw, scale, rc, Ho, Wo, hw_low, flags,
-                      tile=(8, 8), stats=None):
+                      tile=(8, 8), stats=None, row_walk=False):
     """off (rows, G*P*2), msk (rows, G*P), gout (N,Ho,Wo,G*gc) float arrays; hw_low (n,2) / flags (n,) from the oracle's
-    index() (the integer part of the contract).  Returns grad_input (N,H,W,G*gc) float64."""
+    index() (the integer part of the contract).  Returns grad_input (N,H,W,G*gc) float64.
+    row_walk=True models dcnv3_bwd_fused.cuh instead (768-cell window, one visit per sample along each cell row, two
+    column slots -- even / odd destination column -- flushed when the row's column moves on)."""
+    cells_max = 768 if row_walk else CELLS
     P = kh * kw - rc
     C = G * gc
     gin = np.zeros((N, H, W, C))
@@ -46,7 +49,7 @@ def grad_input_binned(off, msk, gout, N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh
                     mn_h, mx_h = min(s[0] for s in samples), max(s[0] for s in samples)
                     mn_w, mx_w = min(s[1] for s in samples), max(s[1] for s in samples)
                     WWa = min(mx_w - mn_w + 1, WIN_W)
-                    WHa = min(mx_h - mn_h + 1, CELLS // WWa)
+                    WHa = min(mx_h - mn_h + 1, cells_max // WWa)
                     NCa = WHa * WWa
                     bins = [[] for _ in range(NCa)]
                     for s in samples:
@@ -63,6 +66,45 @@ def grad_input_binned(off, msk, gout, N, H, W, G, gc, kh, kw, sh, sw, ph, pw, dh
                                 stats["overflow"] = stats.get("overflow", 0) + 1
                     start = np.concatenate([[0], np.cumsum([len(x) for x in bins])])
                     srt = [rec for cell in bins for rec in cell]
+                    if row_walk:
+                        for row in range(WHa):
+                            i, end = start[row * WWa], start[(row + 1) * WWa]
+                            if i == end:
+                                continue
+                            y = mn_h + row
+                            acc = {0: [np.zeros(gc), np.zeros(gc)], 1: [np.zeros(gc), np.zeros(gc)]}   # slot -> [top, bottom]
+                            cur = {0: -2, 1: -1}
+
+                            def flush(slot):
+                                c = cur[slot]
+                                x = mn_w + c
+                                if c < 0 or x < 0 or x >= W:
+                                    return
+                                for dy in (0, 1):
+                                    if 0 <= y + dy < H and np.any(acc[slot][dy] != 0):
+                                        gin[b, y + dy, x, g * gc:(g + 1) * gc] += acc[slot][dy]
+                                        if stats is not None:
+                                            stats["flush_lines"] = stats.get("flush_lines", 0) + 1
+                            for k in range(i, end):
+                                lh, lw, m, col, gv = srt[k]
+                                odd = col & 1
+                                d = {0: col + odd, 1: col + 1 - odd}
+                                for slot in (0, 1):
+                                    if d[slot] != cur[slot]:
+                                        flush(slot)
+                                        acc[slot] = [np.zeros(gc), np.zeros(gc)]
+                                        cur[slot] = d[slot]
+                                hw = 1 - lw
+                                am, bm = (1 - lh) * m, lh * m
+                                w = {0: lw if odd else hw, 1: hw if odd else lw}
+                                for slot in (0, 1):
+                                    acc[slot][0] += am * w[slot] * gv
+                                    acc[slot][1] += bm * w[slot] * gv
+                            flush(0)
+                            flush(1)
+                        if stats is not None:
+                            stats["corner_lines"] = stats.get("corner_lines", 0) + 4 * len(samples)
+                        continue
                     BW, BH = (WWa + 2) >> 1, (WHa + 2) >> 1
                     for blk in range(BH * BW):
                         bi, bj = divmod(blk, BW)

@@ -323,7 +323,8 @@ def bwd_options():
 
 
 @pytest.mark.parametrize("mode,th,tw,nt", [(0, 8, 8, 192), (1, 8, 8, 192), (1, 8, 8, 128), (1, 16, 16, 256), (1, 4, 8, 192),
-                                           (1, 16, 8, 256), (1, 2, 2, 192)])
+                                           (1, 16, 8, 256), (1, 2, 2, 192), (2, 8, 8, 192), (2, 4, 8, 192), (2, 16, 16, 192),
+                                           (2, 2, 2, 192)])
 @pytest.mark.parametrize("spec", ORACLE_CASES, ids=[c[0] for c in ORACLE_CASES])
 def test_backward_variants_vs_c_oracle(ops, O, bwd_options, spec, mode, th, tw, nt):
     """Every backward variant the tuning knobs can select against the C oracle: f32 1e-4, bf16 8e-3 on rounded inputs."""
@@ -346,11 +347,12 @@ def test_backward_variants_vs_c_oracle(ops, O, bwd_options, spec, mode, th, tw, 
         assert _rel(gi, rgi) < BF16_TOL and _rel(go, rgo) < BF16_TOL and _rel(gm, rgm) < BF16_TOL
 
 
+@pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("std", [3.0, 30.0, 300.0])
-def test_binned_grad_input_window_overflow(ops, O, bwd_options, std):
-    """Offsets far beyond the 32-cell window of the binned kernel: the per-sample fallback scatter must give the same sums."""
+def test_binned_grad_input_window_overflow(ops, O, bwd_options, std, mode):
+    """Offsets far beyond the 32-cell window of the aggregating kernels: the per-sample fallback scatter must give the same sums."""
     lib = bwd_options
-    lib.gp_set_option(OPT_BWD_MODE, 1)
+    lib.gp_set_option(OPT_BWD_MODE, mode)
     gen = torch.Generator().manual_seed(13)
     N, H, W, G, gc = 2, 80, 72, 2, 32
     inp = torch.randn(N, H, W, G * gc, generator=gen)
@@ -375,7 +377,7 @@ def test_backward_elementwise_with_absolute_floor(ops, O, bwd_options):
         out = ops.dcnv3_forward(inp.cuda(), off.cuda(), m.cuda(), *args, 256, 0).cpu().double()
         assert ((out - ref_out).abs() <= 1e-4 * ref_out.abs() + 1e-5 * ref_out.abs().max()).all()
         refs = O.backward(inp.double(), off.double(), m.double(), gout.double(), *args, 0)
-        for mode in (0, 1):
+        for mode in (0, 1, 2):
             bwd_options.gp_set_option(OPT_BWD_MODE, mode)
             got = ops.dcnv3_backward(inp.cuda(), off.cuda(), m.cuda(), *args, gout.cuda(), 256, 0)
             for g_, r_, nm in zip(got, refs, ("grad_input", "grad_offset", "grad_mask")):

@@ -26,8 +26,9 @@ CASES = [  # N, H, W, G, gc, k, s, pad, dil, scale, rc, offset std / kind, full-
 ]
 
 
+@pytest.mark.parametrize("row_walk", [False, True], ids=["blocks(gin_binned)", "row_walk(bwd_fused)"])
 @pytest.mark.parametrize("spec", CASES)
-def test_binned_model_matches_oracle(O, spec):
+def test_binned_model_matches_oracle(O, spec, row_walk):
     N, H, W, G, gc, k, s, pad, d, scale, rc, dist, full = spec
     gen = torch.Generator().manual_seed(3)
     Ho, Wo = O.out_size(H, k, s, pad, d), O.out_size(W, k, s, pad, d)
@@ -47,7 +48,7 @@ def test_binned_model_matches_oracle(O, spec):
     hw, fl = O.index(off, N, H, W, k, k, s, s, pad, pad, d, d, G, scale, rc)
     st = {}
     mine = grad_input_binned(off.numpy(), m.numpy(), gout.numpy(), N, H, W, G, gc, k, k, s, s, pad, pad, d, d, scale, rc,
-                             Ho, Wo, hw.numpy(), fl.numpy(), stats=st)
+                             Ho, Wo, hw.numpy(), fl.numpy(), stats=st, row_walk=row_walk)
     assert np.abs(mine - gi.numpy()).max() / np.abs(gi.numpy()).max() < 2e-5
     assert st["flush_lines"] < st["corner_lines"]          # the point of the exercise: fewer reductions than corners
     if dist == "far":
