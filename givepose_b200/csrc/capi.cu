@@ -9,6 +9,8 @@
 #include "dcnv3_kernels.cuh"
 #include "dcnv3_gin_binned.cuh"
 #include "dcnv3_bwd_fused.cuh"
+#include "dcnv3_fwd_rows.cuh"
+#include "tc_common.cuh"
 
 namespace gp {
 unsigned long long g_launches = 0;
@@ -304,6 +306,51 @@ static void launch_bwd_generic(const void *in, const void *off, const void *msk,
     count_launch();
 }
 
+// ---- forward with TMA-staged offset / mask rows (dcnv3_fwd_rows.cuh): 3x3 kernels ------------------------------------------
+// 3-D row tensor {row values, Wo, N*Ho} of `pitch` elements per pixel; box = {bw values, tile_w, tile_h}
+static bool make_rows_map(CUtensorMap *map, const void *base, int dtype, long long inner, long long pitch, const KParams &p, int bw) {
+    tc::EncodeTiledFn fn = tc::encode_fn();
+    if (!fn) return false;
+    const size_t es = elem_size(dtype);
+    const cuuint64_t dims[3] = {(cuuint64_t)inner, (cuuint64_t)p.Wo, (cuuint64_t)p.N * p.Ho};
+    const cuuint64_t strides[2] = {(cuuint64_t)pitch * es, (cuuint64_t)pitch * es * p.Wo};
+    const cuuint32_t box[3] = {(cuuint32_t)bw, (cuuint32_t)p.tile_w, (cuuint32_t)p.tile_h};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUtensorMapDataType dt = dtype == GP_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                   : dtype == GP_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    return fn(map, dt, 3, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// true: launched.  false: this call keeps the per-thread row reads of dcnv3_fwd_tile (shape / alignment outside the TMA rules).
+template <typename T, int VEC, bool SOFTMAX>
+static bool launch_fwd_rows(const void *in, const void *off, const void *msk, void *out, const KParams &p, int L, int dtype,
+                            cudaStream_t st) {
+    if (p.P != 9 || p.remove_center || (L != 4 && L != 8 && L != 16)) return false;
+    const size_t es = sizeof(T);
+    if ((p.off_q * es) % 16 || (p.msk_q * es) % 16 || !aligned16(off) || !aligned16(msk)) return false;   // TMA: 16-byte strides / base
+    if ((long long)p.N * p.Ho >= (1ll << 31) || p.tile_w > 256 || p.tile_h > 256) return false;
+    const int per16 = (int)(16 / es);
+    const int bw_off = (p.gs * 18 + per16 - 1) / per16 * per16, bw_msk = (p.gs * 9 + per16 - 1) / per16 * per16;
+    if (bw_off > 256) return false;
+    const size_t sm = fwd_rows_smem(p.tile_h * p.tile_w, p.gs, bw_off, bw_msk, (int)es);
+    if (sm > 48 * 1024) return false;
+    CUtensorMap mo, mm;
+    if (!make_rows_map(&mo, off, dtype, (long long)p.G * 18, p.off_q, p, bw_off) ||
+        !make_rows_map(&mm, msk, dtype, (long long)p.G * 9, p.msk_q, p, bw_msk))
+        return false;
+    const unsigned grid = tile_grid(p);
+#define GP_FWDR(LL) dcnv3_fwd_rows<T, VEC, LL, SOFTMAX><<<grid, kTileThreads, sm, st>>>((const T *)in, (T *)out, mo, mm, p, bw_off, bw_msk)
+    switch (L) {
+        case 4: GP_FWDR(4); break;
+        case 8: GP_FWDR(8); break;
+        case 16: GP_FWDR(16); break;
+    }
+#undef GP_FWDR
+    count_launch();
+    return true;
+}
+
 // pitch > 0: `off` points at packed rows [G*P*2 offsets | G*P mask values | padding] of `pitch` elements per pixel
 template <bool SOFTMAX>
 static int forward_impl(const void *in, const void *off, const void *msk, void *out, const gp_dcnv3_desc *d, int dtype,
@@ -321,6 +368,13 @@ static int forward_impl(const void *in, const void *off, const void *msk, void *
     int L = 0, vec = 0;
     if (pitch && !plan_tiled(p, dtype, &L, &vec)) return GP_ERR_UNSUPPORTED;   // packed rows: tiled kernels only
     if (plan_tiled(p, dtype, &L, &vec)) {
+        bool done = false;
+        if (g_tune.fwd_mode == 1) {
+            if (dtype == GP_F32) done = launch_fwd_rows<float, 4, SOFTMAX>(in, off, msk, out, p, L, dtype, st);
+            else if (dtype == GP_BF16 && vec == 8) done = launch_fwd_rows<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, dtype, st);
+            else if (dtype == GP_F16 && vec == 8) done = launch_fwd_rows<__half, 8, SOFTMAX>(in, off, msk, out, p, L, dtype, st);
+        }
+        if (done) return (int)cudaGetLastError();
         if (dtype == GP_F32) launch_fwd_tile<float, 4, SOFTMAX>(in, off, msk, out, p, L, st);
         else if (dtype == GP_BF16 && vec == 8) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
         else if (dtype == GP_BF16) launch_fwd_tile<__nv_bfloat16, 4, SOFTMAX>(in, off, msk, out, p, L, st);

@@ -107,20 +107,20 @@ int gp_smallk_dwconv3x3_ln_gelu(const void *x, const float *w_eff, const float *
     return (int)cudaGetLastError();
 }
 
-int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N, int H,
-                     int W, int C, int G, float eps, int act, int dtype, void *stream) {
+static int groupnorm_act_impl(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N, int H,
+                              int W, int C, int G, float eps, int act, int dtype, void *stream, bool have_stats) {
     if (!x || !y || !stats || !gamma || !beta) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || C <= 0 || G <= 0 || C % G || (C / G) % 4 || C / 4 > 256) return GP_ERR_SHAPE;
     if (act < 0 || act > 2) return GP_ERR_UNSUPPORTED;
     if (dtype != GP_F32 && C % 8) return GP_ERR_SHAPE;   // 16-byte channel vectors
     if (!al16(x) || !al16(y) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
-    if (stats_floats < gp_groupnorm_workspace_floats(N, H, W, G)) return GP_ERR_WORKSPACE;
+    if (stats_floats < (have_stats ? (size_t)N * G * 2 : gp_groupnorm_workspace_floats(N, H, W, G))) return GP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
     int appc = 0;
     const dim3 agrid = slab_grid(N, HW, 16, &appc);
 #define GP_GN_APPLY(TT, AA) gn_apply_kernel<TT, AA><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, (TT *)y, HW, C, G, eps, appc)
-#define GP_GN(TT) do { gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
+#define GP_GN(TT) do { if (!have_stats) gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
                        if (act == ACT_RELU) GP_GN_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GN_APPLY(TT, ACT_GELU); \
                        else GP_GN_APPLY(TT, ACT_NONE); } while (0)
     switch (dtype) {
@@ -131,6 +131,26 @@ int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, 
     }
 #undef GP_GN
 #undef GP_GN_APPLY
+    count_launch();
+    return (int)cudaGetLastError();
+}
+
+int gp_groupnorm_act(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta, int N, int H,
+                     int W, int C, int G, float eps, int act, int dtype, void *stream) {
+    return groupnorm_act_impl(x, y, stats, stats_floats, gamma, beta, N, H, W, C, G, eps, act, dtype, stream, false);
+}
+
+// apply pass only: stats[0 .. N*G*2) already holds (mean, rstd) per (n, group), e.g. from gp_conv3x3_gn_bf16 + gp_groupnorm_finalize
+int gp_groupnorm_apply(const void *x, void *y, const float *stats, size_t stats_floats, const float *gamma, const float *beta, int N, int H,
+                       int W, int C, int G, float eps, int act, int dtype, void *stream) {
+    return groupnorm_act_impl(x, y, const_cast<float *>(stats), stats_floats, gamma, beta, N, H, W, C, G, eps, act, dtype, stream, true);
+}
+
+// (mean, rstd) per (n, group) from per-slab (sum, sum of squares) partials laid out [N][slabs][G][2], summed in slab order
+int gp_groupnorm_finalize(const float *partial, float *stats, int N, int G, int slabs, long long count, float eps, void *stream) {
+    if (!partial || !stats) return GP_ERR_NULL;
+    if (N <= 0 || G <= 0 || slabs <= 0 || count <= 0) return GP_ERR_SHAPE;
+    gn_finalize_kernel<<<(N * G + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partial, stats, N * G, G, slabs, 1.f / (float)count, eps);
     count_launch();
     return (int)cudaGetLastError();
 }
@@ -204,20 +224,20 @@ int gp_groupnorm_act_backward(const void *x, const void *dy, const float *stats,
     return (int)cudaGetLastError();
 }
 
-int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
-                             const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
-                             int dtype, void *stream) {
+static int groupnorm_act_conv1x1_impl(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                                      const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                                      int dtype, void *stream, bool have_stats) {
     if (!x || !y || !stats || !gamma || !beta || !w || !bias) return GP_ERR_NULL;
     if (N <= 0 || N > 65535 || H <= 0 || W <= 0 || G <= 0 || C % G || (C / G) % 4) return GP_ERR_SHAPE;
     if (C != 256 || OC != 3 || act < 0 || act > 2) return GP_ERR_UNSUPPORTED;   // the decoder's out_layer
     if (!al16(x) || !al16(gamma) || !al16(beta)) return GP_ERR_ALIGN;
-    if (stats_floats < gp_groupnorm_workspace_floats(N, H, W, G)) return GP_ERR_WORKSPACE;
+    if (stats_floats < (have_stats ? (size_t)N * G * 2 : gp_groupnorm_workspace_floats(N, H, W, G))) return GP_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int HW = H * W;
     int appc = 0;
     const dim3 agrid = slab_grid(N, HW, 8, &appc);
 #define GP_GNC_APPLY(TT, AA) gn_act_conv1x1_kernel<TT, AA, 8, 3><<<agrid, 256, 0, st>>>((const TT *)x, stats, gamma, beta, w, bias, (TT *)y, HW, G, eps, appc)
-#define GP_GNC(TT) do { gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
+#define GP_GNC(TT) do { if (!have_stats) gn_statistics<TT>(x, stats, N, HW, C, G, eps, st); \
                         if (act == ACT_RELU) GP_GNC_APPLY(TT, ACT_RELU); else if (act == ACT_GELU) GP_GNC_APPLY(TT, ACT_GELU); \
                         else GP_GNC_APPLY(TT, ACT_NONE); } while (0)
     switch (dtype) {
@@ -230,6 +250,19 @@ int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_
 #undef GP_GNC_APPLY
     count_launch();
     return (int)cudaGetLastError();
+}
+
+int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                             const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                             int dtype, void *stream) {
+    return groupnorm_act_conv1x1_impl(x, y, stats, stats_floats, gamma, beta, w, bias, N, H, W, C, G, eps, act, OC, dtype, stream, false);
+}
+
+int gp_groupnorm_apply_conv1x1(const void *x, void *y, const float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                               const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                               int dtype, void *stream) {
+    return groupnorm_act_conv1x1_impl(x, y, const_cast<float *>(stats), stats_floats, gamma, beta, w, bias, N, H, W, C, G, eps, act, OC, dtype,
+                                      stream, true);
 }
 
 int gp_upsample_bilinear2x(const void *x, void *y, int N, int H, int W, int C, int dtype, void *stream) {

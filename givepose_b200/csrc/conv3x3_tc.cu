@@ -1,0 +1,291 @@
+// givepose_b200 -- the coordinate-map decoder's 3x3 convolutions as a hand-written tcgen05 implicit GEMM (sm_100a).
+//
+// Replaces the cuDNN convolutions of TopDownXyzHead's ConvModules (network/xyz_head.py:195-366: six Conv2d(256, 256, 3, padding=1,
+// bias=False) per head at 16x16, 32x32 and 64x64, each followed by GroupNorm(32) + GELU, network/torch_utils/layers/
+// conv_module.py:57-234) -- 96 % of the decoder's FLOPs -- and produces the GroupNorm statistics in the same pass:
+//
+//     y[(n,h,w), o] = sum_{ky,kx,c} x[n, h+ky-1, w+kx-1, c] * wgt[o, ky, kx, c]       bf16 operands, fp32 accumulation in TMEM
+//     partial[n][slab][g][0..1] = (sum, sum of squares) of the fp32 accumulators of group g over the slab's 64 pixels
+//
+// Implicit GEMM: M = N*H*W output pixels, N = 256 output channels, K = 9 taps x Cin.  No im2col buffer exists anywhere: the A
+// operand of tap (ky, kx) and channel block kc for 128 consecutive output pixels (128/W image rows) is ONE 4-D TMA box
+// {64 channels, W, 128/W rows, 1 image} at coordinates {64 kc, kx-1, h0+ky-1, n} of the channel-last activation; coordinates
+// that fall outside the image (-1 or H / W) are zero-filled by TMA, which is exactly the zero padding, and the box lands in
+// shared memory as 128 rows of 128 bytes with the 128-byte swizzle the tensor core's K-major descriptor expects.
+//
+// CTA tile = 256 pixels x 256 channels: two M128 x N256 accumulators = all 512 TMEM columns, so every 32 KB weight block
+// (256 rows x 64 K) that comes through shared memory feeds 2 x 4 MMAs -- 64 KB of operands per 1024 tensor-pipe cycles, the same
+// operand traffic per FLOP as a cta_group::2 pair with 256 x 256 tiles, without a cluster.  Persistent CTAs (one per SM, 192
+// threads, warp-specialised):
+//   warp 0     TMA producer: per K block two 4-D activation boxes (the tile's two halves) + one 2-D weight box into a ring of
+//              three 64 KB stages, completion on mbarriers (expect_tx); runs ahead across tile boundaries
+//   warp 1     TMEM allocation (512 columns); one elected thread issues tcgen05.mma.cta_group::1.kind::f16 M128 N256 K16,
+//              tcgen05.commit releases the stage / publishes the accumulators
+//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, GroupNorm partial sums of the fp32 values (transposing butterfly
+//              over the 32 rows of the warp: 9 shuffles per 4 groups), bf16 pack, 16-byte global stores; the partials go out in
+//              the [n][slab][g][2] layout gn_finalize_kernel sums in a fixed order (no atomics: bit-reproducible)
+#include "tc_common.cuh"
+
+namespace gp {
+namespace tc {
+namespace conv {
+
+constexpr int BN = 256;                          // output channels = the whole Cout of the decoder
+constexpr int SUB = 2;                           // M128 sub-tiles (accumulators) per CTA tile
+constexpr int TILE_PIX = SUB * BM;               // 256 output pixels per tile
+constexpr int B_BYTES = BN * BK * 2;             // 32 KB weight block
+constexpr int STAGE_BYTES = SUB * A_BYTES + B_BYTES;   // 64 KB
+constexpr int STAGES = 3;
+constexpr int TMEM_COLS = SUB * BN;              // 512: the whole tensor memory of the SM
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr int GN_GROUPS = 32, CPG = BN / GN_GROUPS;   // GroupNorm(32, 256): 8 channels per group
+
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+
+// Sum eight per-lane values over the 32 lanes with a transposing butterfly (4 + 2 + 1 + 2 shuffles).  On return every lane
+// holds the warp total of value index ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1).
+__device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
+    const unsigned full = 0xffffffffu;
+    float a[4], b[2], c;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float keep = h16 ? v[4 + i] : v[i], send = h16 ? v[i] : v[4 + i];
+        a[i] = keep + __shfl_xor_sync(full, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float keep = h8 ? a[2 + i] : a[i], send = h8 ? a[i] : a[2 + i];
+        b[i] = keep + __shfl_xor_sync(full, send, 8);
+    }
+    {
+        const float keep = h4 ? b[1] : b[0], send = h4 ? b[0] : b[1];
+        c = keep + __shfl_xor_sync(full, send, 4);
+    }
+    c += __shfl_xor_sync(full, c, 2);
+    c += __shfl_xor_sync(full, c, 1);
+    return c;
+}
+
+// tiles_per_img = H*W / 256; rows_per_sub = 128 / W image rows per accumulator; kc_blocks = Cin / 64.
+template <bool STATS>
+__global__ void __launch_bounds__(THREADS, 1)
+conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                  __nv_bfloat16 *__restrict__ y, float *__restrict__ partial /*[N][tiles_per_img*4][32][2]*/, int n_tiles,
+                  int tiles_per_img, int rows_per_sub, int kc_blocks) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
+    const uint32_t bars = base + STAGES * STAGE_BYTES;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES), tmem_empty_bar = bars + 8u * (2 * STAGES + 1);
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_k = 9 * kc_blocks;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        mbar_init(tmem_empty_bar, 4);   // one arrival per epilogue warp
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * (SUB * rows_per_sub);
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int tap = kb / kc_blocks, kc = kb - tap * kc_blocks;
+                    const int ky = tap / 3, kx = tap - ky * 3;
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
+                    const uint32_t st = base + s * STAGE_BYTES;
+#pragma unroll
+                    for (int sub = 0; sub < SUB; ++sub)
+                        tma_load_4d(st + sub * A_BYTES, &map_x, full_bar(s), kc * BK, kx - 1, h0 + sub * rows_per_sub + ky - 1, n);
+                    tma_load_2d(st + SUB * A_BYTES, &map_w, full_bar(s), kb * BK, 0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+                mbar_wait(tmem_empty_bar, (lt & 1u) ^ 1u);          // the epilogue has drained the previous tile (first passes)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1u;
+                    mbar_wait(full_bar(s), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = base + s * STAGE_BYTES, b_addr = a_addr + SUB * A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t bd = make_desc(b_addr + k * UMMA_K * 2);
+#pragma unroll
+                        for (int sub = 0; sub < SUB; ++sub)
+                            umma_bf16(tmem_base + sub * BN, make_desc(a_addr + sub * A_BYTES + k * UMMA_K * 2), bd, IDESC, (kb | k) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(s));
+                }
+                umma_commit(tmem_full_bar);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
+        const int q = warp & 3;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+            const int n = tile / tiles_per_img, t_in = tile - n * tiles_per_img;
+            mbar_wait(tmem_full_bar, lt & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+                float st8[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) st8[i] = 0.f;
+#pragma unroll
+                for (int sub = 0; sub < SUB; ++sub) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * BN + c);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    // this lane's output pixel: row 32q + lane of sub-tile `sub`; 32 consecutive channels c .. c+31
+                    __nv_bfloat16 *dst = y + ((size_t)tile * TILE_PIX + sub * BM + q * 32 + lane) * BN + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint32_t pk[4];
+#pragma unroll
+                        for (int t = 0; t < 4; ++t) {
+                            const float a = __uint_as_float(r[j + 2 * t]), b = __uint_as_float(r[j + 2 * t + 1]);
+                            const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                            pk[t] = *reinterpret_cast<const uint32_t *>(&h);
+                        }
+                        *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        if (STATS) {
+                            float s = 0.f, ss = 0.f;
+#pragma unroll
+                            for (int t = 0; t < 8; ++t) {
+                                const float v = __uint_as_float(r[j + t]);
+                                s += v;
+                                ss = fmaf(v, v, ss);
+                            }
+                            st8[(j >> 3) * 2] += s;
+                            st8[(j >> 3) * 2 + 1] += ss;
+                        }
+                    }
+                }
+                if (STATS) {
+                    const float tot = warp_sum8(st8, lane);
+                    if ((lane & 3) == 0) {
+                        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        const int g = (c >> 3) + (idx >> 1);
+                        partial[(((size_t)n * (tiles_per_img * 4) + t_in * 4 + q) * GN_GROUPS + g) * 2 + (idx & 1)] = tot;
+                    }
+                }
+            }
+            // every TMEM read of this tile has completed: hand the accumulators back to the MMA warp
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty_bar);
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
+// channel-last activation (N, H, W, C) bf16 as a 4-D tensor {C, W, H, N}; box = {64 channels, W, rows, 1}: 128 pixels x 128 bytes
+static bool make_act_map(CUtensorMap *map, const void *ptr, int N, int H, int W, int C, int rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+    const cuuint32_t box[4] = {(cuuint32_t)BK, (cuuint32_t)W, (cuuint32_t)rows, 1};
+    const cuuint32_t estr[4] = {1, 1, 1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace conv
+}  // namespace tc
+}  // namespace gp
+
+extern "C" {
+
+size_t gp_conv3x3_gn_slabs(int H, int W) {
+    if (H <= 0 || W <= 0 || (H * W) % gp::tc::conv::TILE_PIX) return 0;
+    return (size_t)(H * W / gp::tc::conv::TILE_PIX) * 4;
+}
+
+int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream) {
+    using namespace gp::tc;
+    using namespace gp::tc::conv;
+    if (!x || !w_packed || !y) return GP_ERR_NULL;
+    if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return GP_ERR_SHAPE;
+    // 128 output pixels = whole image rows (W divides 128), a 256-pixel tile never straddles two images
+    if (Cout != BN || Cin % BK || W > 128 || BM % W || (H * W) % TILE_PIX || H % (SUB * (BM / W))) return GP_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
+    const long long tiles = (long long)N * (H * W / TILE_PIX);
+    if (tiles >= (1ll << 31) / TILE_PIX) return GP_ERR_SHAPE;
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return GP_ERR_UNSUPPORTED;
+    if (!sms_of[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int sms = sms_of[dev];
+    CUtensorMap mx, mw;
+    if (!make_act_map(&mx, x, N, H, W, Cin, BM / W) || !make_map(&mw, w_packed, BN, 9 * Cin, BN)) return GP_ERR_UNSUPPORTED;
+    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (partial)
+        conv3x3_gn_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, (__nv_bfloat16 *)y, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK);
+    else
+        conv3x3_gn_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, (__nv_bfloat16 *)y, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK);
+    gp::g_launches += 1;
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

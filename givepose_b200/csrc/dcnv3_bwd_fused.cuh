@@ -82,7 +82,12 @@ dcnv3_bwd_fused(const T *__restrict__ in, const T *__restrict__ off, const T *__
     for (int k = 0; k < SPT; ++k) {
         const int r = tid + k * NT;
         s_key[k] = -1;
-        if (r < n_rec && s_bf[r].y != 0) {   // flags != 0 <=> the sample is in range (cuh:268-269)
+        bool live = r < n_rec;
+        if (live) {   // build_records leaves the records of tile-overhang units unwritten: never look at them
+            const int ul = P9 ? r / 9 : r / P;
+            live = t.oh0 + (ul >> p.lg_tw) < p.Ho && t.ow0 + (ul & (p.tile_w - 1)) < p.Wo;
+        }
+        if (live && s_bf[r].y != 0) {   // flags != 0 <=> the sample is in range (cuh:268-269)
             const int key = __float_as_int(s_w[r].w);
             s_key[k] = key;
             const int h = (key >> 16) - 1, w = (key & 0xffff) - 1;

@@ -198,6 +198,72 @@ def groupnorm_act_conv1x1(x, gamma, beta, weight, bias, groups=32, eps=1e-5, act
     return y
 
 
+def pack_conv3x3_weight(weight):
+    """``Conv2d(Cin, 256, 3)`` weight (Cout, Cin, 3, 3) -> the K-major bf16 matrix (Cout, 9*Cin), K = (ky, kx, cin), that
+    ``conv3x3_gn_bf16`` reads."""
+    return weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], -1).contiguous().to(torch.bfloat16)
+
+
+def conv3x3_gn_supported(x, cout):
+    """Shapes the tcgen05 implicit-GEMM convolution takes: bf16 channel-last, Cout 256, Cin % 64 == 0, W | 128, H*W % 256 == 0."""
+    if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_cuda:
+        return False
+    N, H, W, C = x.shape
+    return cout == 256 and C % 64 == 0 and W <= 128 and 128 % W == 0 and (H * W) % 256 == 0 and H % (256 // W) == 0
+
+
+def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True):
+    """``Conv2d(Cin, 256, 3, padding=1, bias=False)`` on channel-last bf16 ``x`` (N,H,W,Cin) as a hand-written tcgen05 implicit
+    GEMM (``conv3x3_tc.cu``; ``xyz_head.py:195-366`` / ``conv_module.py:57-234``).  Returns ``(y, stats)``: ``y`` (N,H,W,256)
+    bf16 and, if ``stats``, the GroupNorm(32) ``(mean, rstd)`` pairs [N*32*2] of the fp32 accumulators (for ``groupnorm_apply``)."""
+    _need_cuda("input", x, torch.bfloat16)
+    _need_cuda("weight", w_packed, torch.bfloat16)
+    N, H, W, C = x.shape
+    Cout = w_packed.shape[0]
+    if tuple(w_packed.shape) != (Cout, 9 * C) or not conv3x3_gn_supported(x, Cout) or int(groups) != 32:
+        raise RuntimeError(f"conv3x3_gn_bf16: unsupported shapes {tuple(x.shape)} x {tuple(w_packed.shape)} (groups {groups})")
+    y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device)
+    slabs = lib.gp_conv3x3_gn_slabs(H, W)
+    ws = torch.empty(N * 32 * 2 * (1 + slabs), dtype=torch.float32, device=x.device) if stats else None
+    partial = ws[N * 32 * 2:] if stats else None
+    with torch.cuda.device(x.device):
+        check(lib.gp_conv3x3_gn_bf16(_vp(x), _vp(w_packed), _vp(y), _vp(partial) if stats else None, N, H, W, C, Cout, _stream(x)),
+              "conv3x3_gn_bf16")
+        if stats:
+            check(lib.gp_groupnorm_finalize(_vp(partial), _vp(ws), N, 32, slabs, H * W * (Cout // 32), float(eps), _stream(x)),
+                  "groupnorm_finalize")
+    return y, (ws[:N * 32 * 2] if stats else None)
+
+
+def groupnorm_apply(x, stats, gamma, beta, groups=32, eps=1e-5, act="none", upsample2x=False):
+    """Apply pass of ``groupnorm_act`` with precomputed ``(mean, rstd)`` pairs (``conv3x3_gn_bf16``)."""
+    dt = _nhwc("input", x)
+    for n, t in (("stats", stats), ("gn weight", gamma), ("gn bias", beta)):
+        _need_cuda(n, t, torch.float32)
+    N, H, W, C = x.shape
+    y = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        check(lib.gp_groupnorm_apply(_vp(x), _vp(y), _vp(stats), stats.numel(), _vp(gamma), _vp(beta), N, H, W, C, int(groups), float(eps),
+                                     ACT[act], dt, _stream(x)), "groupnorm_apply")
+    return upsample_bilinear2x(y) if upsample2x else y
+
+
+def groupnorm_apply_conv1x1(x, stats, gamma, beta, weight, bias, groups=32, eps=1e-5, act="gelu"):
+    """``groupnorm_act_conv1x1`` with precomputed ``(mean, rstd)`` pairs."""
+    dt = _nhwc("input", x)
+    for n, t in (("stats", stats), ("gn weight", gamma), ("gn bias", beta), ("out_layer weight", weight), ("out_layer bias", bias)):
+        _need_cuda(n, t, torch.float32)
+    N, H, W, C = x.shape
+    OC = weight.shape[0]
+    if weight.shape != (OC, C) or bias.shape != (OC,):
+        raise RuntimeError("groupnorm_apply_conv1x1: inconsistent weight / bias shapes")
+    y = torch.empty((N, H, W, OC), dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.gp_groupnorm_apply_conv1x1(_vp(x), _vp(y), _vp(stats), stats.numel(), _vp(gamma), _vp(beta), _vp(weight), _vp(bias), N, H, W,
+                                             C, int(groups), float(eps), ACT[act], OC, dt, _stream(x)), "groupnorm_apply_conv1x1")
+    return y
+
+
 LIN_ACT = {"none": 0, "lrelu": 1, "relu": 2}
 
 

@@ -30,6 +30,7 @@ What runs where (inference, ``torch.no_grad``):
 from __future__ import annotations
 
 import contextlib
+import os
 from dataclasses import dataclass
 
 import torch
@@ -38,6 +39,9 @@ import torch.nn.functional as F
 
 from . import ops
 from .functions import DCNv3Function, dcnv3_forward, dcnv3_forward_packed
+
+# decoder 3x3 convolutions at bf16 inference: 'tc' = the hand-written tcgen05 implicit GEMM (conv3x3_tc.cu), 'cudnn' = library
+DECODER_CONV = os.environ.get("GP_DECODER_CONV", "tc")
 
 
 @dataclass
@@ -436,7 +440,22 @@ class ConvModule(nn.Module):
         self.activate = nn.GELU()
         nn.init.kaiming_normal_(self.conv.weight, a=0, mode="fan_out", nonlinearity="relu")
 
+    def _tc(self, x):
+        """bf16 inference: the hand-written tcgen05 implicit-GEMM convolution (GroupNorm statistics from its epilogue)."""
+        return (DECODER_CONV == "tc" and _fused(x) and self.conv.kernel_size == (3, 3) and self.conv.stride == (1, 1)
+                and self.conv.padding == (1, 1) and self.conv.dilation == (1, 1) and self.conv.groups == 1 and self.conv.bias is None
+                and self.norm.num_groups == 32 and ops.conv3x3_gn_supported(x, self.conv.out_channels))
+
+    def conv_gn_stats(self, x):
+        """conv -> (y, (mean, rstd) pairs of GroupNorm(32) over y); only valid when ``_tc(x)``."""
+        return ops.conv3x3_gn_bf16(x.contiguous(), _cached(self.conv.weight, torch.bfloat16, ops.pack_conv3x3_weight, "k-major"),
+                                   self.norm.num_groups, self.norm.eps)
+
     def forward_nhwc(self, x, upsample2x=False):
+        if self._tc(x):
+            y, stats = self.conv_gn_stats(x)
+            return ops.groupnorm_apply(y, stats, _cached(self.norm.weight, torch.float32), _cached(self.norm.bias, torch.float32),
+                                       self.norm.num_groups, self.norm.eps, "gelu", upsample2x)
         return _gn_act_nhwc(_conv_nhwc(x, self.conv), self.norm, "gelu", upsample2x)
 
     def forward(self, x):
@@ -476,6 +495,12 @@ class TopDownXyzHead(nn.Module):
         if _fused(x) and x.shape[-1] == 256 and self.out_layer.out_channels == 3:
             # last ConvModule: conv -> [GN -> GELU -> out_layer 1x1] in one pass; the 256-channel activation is never written
             last = fs[10]
+            gnw, gnb = _cached(last.norm.weight, torch.float32), _cached(last.norm.bias, torch.float32)
+            ow = _cached(self.out_layer.weight, torch.float32, lambda w: w.flatten(1), "rows")
+            if last._tc(x):
+                y, stats = last.conv_gn_stats(x)
+                return ops.groupnorm_apply_conv1x1(y, stats, gnw, gnb, ow, _cached(self.out_layer.bias, torch.float32),
+                                                   last.norm.num_groups, last.norm.eps, "gelu")
             return ops.groupnorm_act_conv1x1(_conv_nhwc(x, last.conv).contiguous(), _cached(last.norm.weight, torch.float32),
                                              _cached(last.norm.bias, torch.float32),
                                              _cached(self.out_layer.weight, torch.float32, lambda w: w.flatten(1), "rows"),

@@ -192,6 +192,29 @@ int gp_groupnorm_act_conv1x1(const void *x, void *y, float *stats, size_t stats_
                              const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
                              int dtype, void *stream);
 
+/* Apply pass of gp_groupnorm_act / gp_groupnorm_act_conv1x1 with (mean, rstd) per (n, group) already in stats[0 .. N*G*2)
+ * (stats_floats >= N*G*2), e.g. from gp_conv3x3_gn_bf16 + gp_groupnorm_finalize: the statistics pass over x is skipped. */
+int gp_groupnorm_apply(const void *x, void *y, const float *stats, size_t stats_floats, const float *gamma, const float *beta, int N,
+                       int H, int W, int C, int G, float eps, int act, int dtype, void *stream);
+int gp_groupnorm_apply_conv1x1(const void *x, void *y, const float *stats, size_t stats_floats, const float *gamma, const float *beta,
+                               const float *w, const float *bias, int N, int H, int W, int C, int G, float eps, int act, int OC,
+                               int dtype, void *stream);
+/* stats[n][g] = (mean, rstd) from per-slab partial (sum, sum of squares) pairs laid out [N][slabs][G][2] (fp32), summed in slab
+ * order (bit-reproducible); count = elements per (n, group) = H*W*C/G. */
+int gp_groupnorm_finalize(const float *partial, float *stats, int N, int G, int slabs, long long count, float eps, void *stream);
+
+/* The coordinate-map decoder's 3x3 convolutions (network/xyz_head.py:195-366 -> ConvModule, network/torch_utils/layers/
+ * conv_module.py:57-234: Conv2d(Cin, 256, 3, stride 1, padding 1, bias=False)) as a hand-written tcgen05 implicit GEMM with the
+ * GroupNorm(32) statistics of the result produced in the epilogue (conv3x3_tc.cu).
+ *   x (N,H,W,Cin) bf16 channel-last; w_packed [256][3][3][Cin] bf16 (= conv.weight.permute(0,2,3,1)); y (N,H,W,256) bf16.
+ *   partial: NULL, or N * gp_conv3x3_gn_slabs(H,W) * 32 * 2 floats that receive the (sum, sum of squares) of the fp32
+ *   accumulators per (image, 64-pixel slab, group of 8 channels) in the layout gp_groupnorm_finalize reads.
+ * Supported: Cout == 256, Cin % 64 == 0, W in {16, 32, 64, 128} with H*W a multiple of 256 (whole 128-pixel row blocks).
+ * fp32 accumulation over K = 9*Cin in tensor memory; zero padding comes from TMA's out-of-bounds fill. */
+size_t gp_conv3x3_gn_slabs(int H, int W);
+int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout,
+                       void *stream);
+
 /* ---- RoI input pipeline in front of PoseNet.forward -------------------------------------------
  * Replaces the per-RoI host work of the reference's loaders (evaluation/load_data_eval.py:256-289,
  * datasets/load_data_nocs.py:277-305): crop_resize_by_warp_affine (tools/dataset_utils.py:101-114 = get_affine_transform
@@ -285,7 +308,8 @@ int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);
  *                            visited once, ~3x fewer reductions), so the two phases overlap across the CTAs of an SM
  *   GP_OPT_GIN_TILE_H/W  output tile of the binned grad_input kernel (powers of two, default 8 x 8)
  *   GP_OPT_GIN_THREADS   its CTA size: 128, 192 (default) or 256
- *   GP_OPT_FWD_MODE      0 = round-1 forward kernel, 1 = packed-record forward (default) */
+ *   GP_OPT_FWD_MODE      0 = dcnv3_fwd_tile (per-thread offset / mask row reads, 24-byte records), 1 = dcnv3_fwd_rows for 3x3
+ *                        kernels (default): rows staged by TMA, 16-byte records; other shapes always take mode 0 */
 enum gp_option { GP_OPT_BWD_MODE = 0, GP_OPT_GIN_TILE_H = 1, GP_OPT_GIN_TILE_W = 2, GP_OPT_GIN_THREADS = 3,
                  GP_OPT_FWD_MODE = 4 };
 int gp_set_option(int key, int value);

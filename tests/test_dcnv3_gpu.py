@@ -316,7 +316,7 @@ OPT_BWD_MODE, OPT_GIN_TH, OPT_GIN_TW, OPT_GIN_NT = 0, 1, 2, 3
 @pytest.fixture
 def bwd_options():
     from givepose_b200._lib import lib
-    saved = [lib.gp_get_option(k) for k in range(4)]
+    saved = [lib.gp_get_option(k) for k in range(5)]
     yield lib
     for k, v in enumerate(saved):
         lib.gp_set_option(k, v)
@@ -428,3 +428,56 @@ def test_forward_inf_next_to_the_border_documented_deviation(ops, O):
     assert (~torch.isfinite(got[~fin])).all()              # where the reference overflows, so do we
     # rows far from the poisoned border (no footprint can reach image row 0 with |offset| < 1.5 + kernel reach 1) are exact
     assert torch.isfinite(got[:, 5:]).all() and _rel(got[:, 5:], ref[:, 5:]) < 1e-5
+
+
+# ---- forward variants: GP_OPT_FWD_MODE 0 = dcnv3_fwd_tile (per-thread row reads, 24-byte records), 1 = dcnv3_fwd_rows (3x3: offset /
+# mask rows staged by TMA, 16-byte rank-one records; shapes outside its rules fall back to mode 0 inside the library) ----------------
+
+OPT_FWD_MODE = 4
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("spec", ORACLE_CASES, ids=[c[0] for c in ORACLE_CASES])
+def test_forward_modes_vs_c_oracle(ops, O, bwd_options, spec, mode):
+    """Both forward kernels against the C oracle: fp32 1e-5, bf16 / f16 on rounded inputs, the fused softmax, and the packed
+    offset||logits rows of the fused offset/mask Linear (pitch padded to a multiple of 8 elements)."""
+    name, N, H, W, G, gc, k, s, pad, dil, scale, rc, dist, full = spec
+    bwd_options.gp_set_option(OPT_FWD_MODE, mode)
+    gen = torch.Generator().manual_seed(11)
+    inp, off, m, _ = _rand_case(gen, N, H, W, G, gc, k, s, pad, dil, rc, dist, full)
+    args = (k, k, s, s, pad, pad, dil, dil, G, gc, scale)
+    ref = O.forward(inp, off, m, *args, rc)
+    assert _rel(ops.dcnv3_forward(inp.cuda(), off.cuda(), m.cuda(), *args, 256, rc), ref) < 1e-5
+    P = k * k - rc
+    logits = torch.randn(*m.shape[:-1], G, P, generator=gen) * 2
+    sm = torch.softmax(logits, -1).reshape(m.shape)
+    ref_sm = O.forward(inp, off, sm, *args, rc)
+    out_sm = ops.dcnv3_forward(inp.cuda(), off.cuda(), logits.reshape(m.shape).contiguous().cuda(), *args, 256, rc, mask_is_logits=True)
+    assert _rel(out_sm, ref_sm) < 1e-5
+    if gc <= 128:
+        from givepose_b200.functions import dcnv3_forward_packed
+        pitch = (G * P * 3 + 7) // 8 * 8
+        packed = torch.zeros(*off.shape[:-1], pitch)
+        packed[..., :G * P * 2] = off
+        packed[..., G * P * 2:G * P * 3] = logits.reshape(m.shape)
+        assert _rel(dcnv3_forward_packed(inp.cuda(), packed.cuda(), *args, 256, rc), ref_sm) < 1e-5
+        for dtype, tol in ((torch.bfloat16, BF16_TOL), (torch.float16, F16_TOL)):
+            i16, o16, m16, p16 = (t.to(dtype) for t in (inp, off, m, packed))
+            r16 = O.forward(i16.float(), o16.float(), m16.float(), *args, rc)
+            got = ops.dcnv3_forward(i16.cuda(), o16.cuda(), m16.cuda(), *args, 256, rc)
+            assert got.dtype == dtype and _rel(got, r16) < tol
+            l16 = p16[..., G * P * 2:G * P * 3].float().reshape(*m.shape[:-1], G, P)
+            r16p = O.forward(i16.float(), p16[..., :G * P * 2].float().contiguous(), torch.softmax(l16, -1).reshape(m.shape), *args, rc)
+            assert _rel(dcnv3_forward_packed(i16.cuda(), p16.cuda(), *args, 256, rc), r16p) < tol
+
+
+def test_forward_modes_agree_at_full_size(ops, bwd_options, full_size):
+    """Config 2 (N = 64, 64x64x256, G = 8): the TMA-row kernel against the per-thread-row kernel on the same inputs -- the same
+    sums up to the association of the mask-folded bilinear weights (2e-6 of the output's max)."""
+    inp, off, m = full_size[:3]
+    args = (3, 3, 1, 1, 1, 1, 1, 1, 8, 32, 1.0)
+    outs = []
+    for mode in (0, 1):
+        bwd_options.gp_set_option(OPT_FWD_MODE, mode)
+        outs.append(ops.dcnv3_forward(inp, off, m, *args, 256, 0))
+    assert _rel(outs[1], outs[0]) < 2e-6

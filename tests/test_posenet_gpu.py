@@ -22,7 +22,7 @@ BF16_TOL = 1e-1   # bf16 weights + activations (8 mantissa bits) through ~60 lay
 # the outliers are RoIs whose predicted first 6-D axis is short (|a1| = 0.13 .. 0.31 with random-init weights): Gram-Schmidt
 # divides the map noise by that norm.
 BF16_MAP_TOL = 4e-2
-BF16_ROT_MEDIAN_DEG, BF16_ROT_MAX_DEG, BF16_ROT_5DEG_OUTLIERS = 2.0, 10.0, 2
+BF16_ROT_MEDIAN_DEG, BF16_ROT_WELL_DEG = 2.0, 5.0   # see test_posenet_bf16_64_rois_against_fp32 for the conditioning-aware bar
 
 
 def rel(a, b):
@@ -649,19 +649,46 @@ def test_posenet_512_roi_shard_matches_the_oracle(OP):
         assert rel(out[k], ref[k]) < FP32_TOL, (k, rel(out[k], ref[k]))
 
 
+def _tap_rot6(net):
+    """Record the PnP head's raw 6-D rotation output (before Gram-Schmidt) of the next forward."""
+    store, orig = {}, net.pnp_net.forward_nhwc
+
+    def tapped(x):
+        r = orig(x)
+        store["rot6"] = r[0].detach().double().cpu()
+        return r
+
+    net.pnp_net.forward_nhwc = tapped
+    return store
+
+
 def test_posenet_bf16_64_rois_against_fp32(OP):
     """bf16 throughput mode on 64 RoIs against the fp32 parity mode (itself 1e-4 from the reference golden): the stated bf16
-    tolerance of every RoIs/s number -- coordinate maps / translation / size relative to each output's max magnitude,
-    rotations by geodesic angle."""
+    tolerance of every RoIs/s number.  Coordinate maps / translation / size / the raw 6-D rotation output: 4e-2 of each output's
+    max magnitude.  Rotations by geodesic angle: median < 2 deg, every RoI whose 6-D output is well conditioned in the fp32 run
+    (both Gram-Schmidt norms |a1|, |a2 - (a2.x)x| >= 0.5) < 5 deg, and every RoI within what its own 6-D error explains through
+    Gram-Schmidt's conditioning, angle <= 2 |d6| / min(|a1|, |a2_perp|) + 1 deg (rot_reps.py:34-55 divides by those norms; with
+    random-init weights some RoIs predict |a1| ~ 0.13, which turns a 2e-2 map-level error into ~10 deg)."""
     data = OP.make_inputs(64, seed=0)
     _, n32 = build(OP, "o1", precision="fp32")
     _, n16 = build(OP, "o1", precision="bf16")
+    t16, t32 = _tap_rot6(n16), _tap_rot6(n32)
     with torch.no_grad():
         a, b = n16(data, "cuda"), n32(data, "cuda")
     errs = {k: rel(a[k], b[k]) for k in KEYS if k != "rot"}
+    errs["rot6"] = rel(t16["rot6"], t32["rot6"])
     ang = torch.rad2deg(torch.acos(((torch.einsum("bij,bij->b", a["rot"].double().cpu(), b["rot"].double().cpu()) - 1) / 2).clamp(-1, 1)))
-    print("bf16 vs fp32, 64 RoIs:", errs, "rot median", ang.median().item(), "max", ang.max().item())
+    r6 = t32["rot6"]
+    a1, a2 = r6[:, 0:3], r6[:, 3:6]
+    x = a1 / a1.norm(dim=-1, keepdim=True)
+    cond = torch.minimum(a1.norm(dim=-1), (a2 - (a2 * x).sum(-1, keepdim=True) * x).norm(dim=-1))
+    d6 = (t16["rot6"] - r6).norm(dim=-1)
+    bound = torch.rad2deg(2 * d6 / cond) + 1.0
+    well = cond >= 0.5
+    print("bf16 vs fp32, 64 RoIs:", errs, "rot median", ang.median().item(), "max", ang.max().item(), "well-conditioned RoIs",
+          int(well.sum()), "max among them", ang[well].max().item(), "min cond", cond.min().item())
     for k, v in errs.items():
         assert v < BF16_MAP_TOL, (k, v)
-    assert ang.median() < BF16_ROT_MEDIAN_DEG and ang.max() < BF16_ROT_MAX_DEG, sorted(ang.tolist())[-5:]
-    assert int((ang > 5.0).sum()) <= BF16_ROT_5DEG_OUTLIERS, sorted(ang.tolist())[-5:]
+    assert ang.median() < BF16_ROT_MEDIAN_DEG, ang.median()
+    assert int(well.sum()) >= 32 and ang[well].max() < BF16_ROT_WELL_DEG, sorted(ang[well].tolist())[-5:]
+    assert bool((ang <= bound).all()), [(float(x_), float(y_), float(c_)) for x_, y_, c_ in zip(ang, bound, cond) if x_ > y_]

@@ -28,6 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "sweep_bwd.json"))
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--fwd-only", action="store_true", help="only the forward-mode A/B (mode 0 vs 1) and the mode-0 backward time")
     a = ap.parse_args()
     shapes = [("K_N64", 64, 64, 64, 8, 32, 1, False), ("M_64to32_N256", 256, 64, 64, 4, 64, 2, True)]
     variants = [(8, 8, 192), (8, 8, 128)]
@@ -61,7 +62,7 @@ def main():
                 print(json.dumps(row), flush=True)
                 rows.append(row)
                 lib.gp_set_option(OPT_BWD_MODE, 1)
-                for th, tw, nt in variants:
+                for th, tw, nt in ([] if a.fwd_only else variants):
                     lib.gp_set_option(OPT_GIN_TH, th)
                     lib.gp_set_option(OPT_GIN_TW, tw)
                     lib.gp_set_option(OPT_GIN_NT, nt)
@@ -75,7 +76,7 @@ def main():
                     print(json.dumps(row), flush=True)
                     rows.append(row)
                 lib.gp_set_option(OPT_BWD_MODE, 2)
-                for th, tw in ((8, 8), (4, 8), (8, 4), (4, 4)):
+                for th, tw in (() if a.fwd_only else ((8, 8), (4, 8), (8, 4), (4, 4))):
                     lib.gp_set_option(OPT_GIN_TH, th)
                     lib.gp_set_option(OPT_GIN_TW, tw)
                     got = F.dcnv3_backward(inp, off, m, *args, gout, 256, 0)
