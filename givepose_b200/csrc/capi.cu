@@ -331,7 +331,8 @@ static bool launch_fwd_rows(const void *in, const void *off, const void *msk, vo
     if ((p.off_q * es) % 16 || (p.msk_q * es) % 16 || !aligned16(off) || !aligned16(msk)) return false;   // TMA: 16-byte strides / base
     if ((long long)p.N * p.Ho >= (1ll << 31) || p.tile_w > 256 || p.tile_h > 256) return false;
     const int per16 = (int)(16 / es);
-    const int bw_off = (p.gs * 18 + per16 - 1) / per16 * per16, bw_msk = (p.gs * 9 + per16 - 1) / per16 * per16;
+    // box widths: the CTA's gs*18 / gs*9 values + up to per16-1 leading values (boxes start on 16-byte boundaries), in 16-byte units
+    const int bw_off = (p.gs * 18 + 2 * (per16 - 1)) / per16 * per16, bw_msk = (p.gs * 9 + 2 * (per16 - 1)) / per16 * per16;
     if (bw_off > 256) return false;
     const size_t sm = fwd_rows_smem(p.tile_h * p.tile_w, p.gs, bw_off, bw_msk, (int)es);
     if (sm > 48 * 1024) return false;

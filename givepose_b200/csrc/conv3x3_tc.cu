@@ -7,23 +7,26 @@
 //     y[(n,h,w), o] = sum_{ky,kx,c} x[n, h+ky-1, w+kx-1, c] * wgt[o, ky, kx, c]       bf16 operands, fp32 accumulation in TMEM
 //     partial[n][slab][g][0..1] = (sum, sum of squares) of the fp32 accumulators of group g over the slab's 64 pixels
 //
-// Implicit GEMM: M = N*H*W output pixels, N = 256 output channels, K = 9 taps x Cin.  No im2col buffer exists anywhere: the A
-// operand of tap (ky, kx) and channel block kc for 128 consecutive output pixels (128/W image rows) is ONE 4-D TMA box
-// {64 channels, W, 128/W rows, 1 image} at coordinates {64 kc, kx-1, h0+ky-1, n} of the channel-last activation; coordinates
-// that fall outside the image (-1 or H / W) are zero-filled by TMA, which is exactly the zero padding, and the box lands in
-// shared memory as 128 rows of 128 bytes with the 128-byte swizzle the tensor core's K-major descriptor expects.
+// Implicit GEMM: M = N*H*W output pixels, N = 256 output channels, K = 9 taps x Cin.  No im2col buffer exists anywhere: for a tile
+// of 256 output pixels (256/W image rows) and one (kx, 64-channel block) pair, ONE 4-D TMA box {64 channels, W, 256/W + 2 rows,
+// 1 image} at coordinates {64 kc, kx-1, h0-1, n} of the channel-last activation brings the input slab in; coordinates that fall
+// outside the image (-1 or H / W) are zero-filled by TMA, which is exactly the zero padding.  The slab lands in shared memory as
+// rows of 128 bytes (one pixel x 64 channels) with the 128-byte swizzle the tensor core's K-major descriptor expects, and because
+// one image row is W x 128 bytes = a multiple of the 1024-byte swizzle atom (W >= 8), the A operand of vertical tap ky for the
+// tile's accumulator `sub` is simply the slab at byte offset (sub * 128/W + ky) * W * 128: the three vertical taps re-use the same
+// shared-memory data, which halves the activation traffic through L2 (the first version of this kernel re-loaded every tap and
+// ran at the L2 -> SM throughput cap: 64 KB of operands per 1024 tensor-pipe cycles; this one needs 48 KB per 1024).
 //
 // CTA tile = 256 pixels x 256 channels: two M128 x N256 accumulators = all 512 TMEM columns, so every 32 KB weight block
-// (256 rows x 64 K) that comes through shared memory feeds 2 x 4 MMAs -- 64 KB of operands per 1024 tensor-pipe cycles, the same
-// operand traffic per FLOP as a cta_group::2 pair with 256 x 256 tiles, without a cluster.  Persistent CTAs (one per SM, 192
-// threads, warp-specialised):
-//   warp 0     TMA producer: per K block two 4-D activation boxes (the tile's two halves) + one 2-D weight box into a ring of
-//              three 64 KB stages, completion on mbarriers (expect_tx); runs ahead across tile boundaries
+// (256 rows x 64 K) that comes through shared memory feeds 2 x 4 MMAs.  Persistent CTAs (one per SM, 320 threads, warp-specialised):
+//   warp 0     TMA producer: per (kx, kc) one activation slab into a ring of two, per tap one 2-D weight box into a ring of four
+//              32 KB stages; completion on mbarriers (expect_tx); runs ahead across tile boundaries
 //   warp 1     TMEM allocation (512 columns); one elected thread issues tcgen05.mma.cta_group::1.kind::f16 M128 N256 K16,
-//              tcgen05.commit releases the stage / publishes the accumulators
-//   warps 2-5  epilogue: tcgen05.ld 32 lanes x 32 columns, GroupNorm partial sums of the fp32 values (transposing butterfly
-//              over the 32 rows of the warp: 9 shuffles per 4 groups), bf16 pack, 16-byte global stores; the partials go out in
-//              the [n][slab][g][2] layout gn_finalize_kernel sums in a fixed order (no atomics: bit-reproducible)
+//              tcgen05.commit releases the weight stage / the slab / publishes the accumulators
+//   warps 2-9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32 lanes x 32 columns, GroupNorm partial
+//              sums of the fp32 values (transposing butterfly over the 32 rows of the warp: 9 shuffles per 4 groups), bf16 pack
+//              into a swizzled 2 KB staging block, one TMA bulk tensor store per block; the partials go out in the [n][slab][g][2] layout gn_finalize_kernel sums in a fixed order
+//              (no atomics: bit-reproducible)
 #include "tc_common.cuh"
 
 namespace gp {
@@ -33,13 +36,18 @@ namespace conv {
 constexpr int BN = 256;                          // output channels = the whole Cout of the decoder
 constexpr int SUB = 2;                           // M128 sub-tiles (accumulators) per CTA tile
 constexpr int TILE_PIX = SUB * BM;               // 256 output pixels per tile
-constexpr int B_BYTES = BN * BK * 2;             // 32 KB weight block
-constexpr int STAGE_BYTES = SUB * A_BYTES + B_BYTES;   // 64 KB
-constexpr int STAGES = 3;
+constexpr int B_BYTES = BN * BK * 2;             // 32 KB weight block: one tap x 64 input channels x 256 output channels
+constexpr int B_STAGES = 3;
+constexpr int MAX_W = 64;                        // widest image row: the slab holds 256/W + 2 rows of W pixels
+constexpr int SLAB_BYTES = (TILE_PIX + 2 * MAX_W) * BK * 2;   // 48 KB
+constexpr int SLABS = 2;
+constexpr int CONV_THREADS = 320;                // producer warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = SUB * BN;              // 512: the whole tensor memory of the SM
-constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)STAGES * STAGE_BYTES + 256 /*barriers*/;
+constexpr int OUT_BUF_BYTES = 32 * 32 * 2;       // epilogue staging: 32 rows x 32 channels bf16 per TMA store, two buffers per warp
+constexpr int OUT_BYTES = 8 * 2 * OUT_BUF_BYTES; // 32 KB
+constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)SLABS * SLAB_BYTES + (size_t)B_STAGES * B_BYTES + OUT_BYTES + 256 /*barriers*/;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-constexpr int GN_GROUPS = 32, CPG = BN / GN_GROUPS;   // GroupNorm(32, 256): 8 channels per group
+constexpr int GN_GROUPS = 32;                    // GroupNorm(32, 256): 8 channels per group
 
 __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3) {
     asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
@@ -71,34 +79,44 @@ __device__ __forceinline__ float warp_sum8(const float (&v)[8], int lane) {
     return c;
 }
 
-// tiles_per_img = H*W / 256; rows_per_sub = 128 / W image rows per accumulator; kc_blocks = Cin / 64.
+// tiles_per_img = H*W / 256; rows_per_sub = 128 / W image rows per accumulator; kc_blocks = Cin / 64; row_bytes = W * 128.
 template <bool STATS>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(CONV_THREADS, 1)
 conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                  __nv_bfloat16 *__restrict__ y, float *__restrict__ partial /*[N][tiles_per_img*4][32][2]*/, int n_tiles,
-                  int tiles_per_img, int rows_per_sub, int kc_blocks) {
+                  const __grid_constant__ CUtensorMap map_y, float *__restrict__ partial /*[N][tiles_per_img*4][32][2]*/, int n_tiles,
+                  int tiles_per_img, int rows_per_sub, int kc_blocks, int row_bytes) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // swizzle-128B tiles need 1024-byte alignment
-    const uint32_t bars = base + STAGES * STAGE_BYTES;
-    auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    const uint32_t tmem_full_bar = bars + 8u * (2 * STAGES), tmem_empty_bar = bars + 8u * (2 * STAGES + 1);
-    const uint32_t tmem_slot = bars + 8u * (2 * STAGES + 2);
+    const uint32_t b_base = base + SLABS * SLAB_BYTES;
+    const uint32_t out_base = b_base + B_STAGES * B_BYTES;
+    const uint32_t bars = out_base + OUT_BYTES;
+    auto b_full = [&](int s) { return bars + 8u * s; };
+    auto b_empty = [&](int s) { return bars + 8u * (B_STAGES + s); };
+    auto a_full = [&](int s) { return bars + 8u * (2 * B_STAGES + s); };
+    auto a_empty = [&](int s) { return bars + 8u * (2 * B_STAGES + SLABS + s); };
+    const uint32_t tmem_full_bar = bars + 8u * (2 * B_STAGES + 2 * SLABS), tmem_empty_bar = tmem_full_bar + 8u;
+    const uint32_t tmem_slot = tmem_full_bar + 16u;
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int num_k = 9 * kc_blocks;
+    const int groups = 3 * kc_blocks;                                   // (kx, kc) pairs per tile: one slab each
+    const uint32_t slab_bytes = (uint32_t)(SUB * rows_per_sub + 2) * (uint32_t)row_bytes;
 
     if (warp == 0 && lane == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            mbar_init(full_bar(s), 1);
-            mbar_init(empty_bar(s), 1);
+        for (int s = 0; s < B_STAGES; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+        }
+        for (int s = 0; s < SLABS; ++s) {
+            mbar_init(a_full(s), 1);
+            mbar_init(a_empty(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 4);   // one arrival per epilogue warp
+        mbar_init(tmem_empty_bar, 8);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
@@ -112,21 +130,21 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t ia = 0, ib = 0;   // slabs / weight blocks issued so far, across tiles
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * (SUB * rows_per_sub);
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int tap = kb / kc_blocks, kc = kb - tap * kc_blocks;
-                    const int ky = tap / 3, kx = tap - ky * 3;
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(empty_bar(s), ph ^ 1u);
-                    mbar_expect_tx(full_bar(s), STAGE_BYTES);
-                    const uint32_t st = base + s * STAGE_BYTES;
-#pragma unroll
-                    for (int sub = 0; sub < SUB; ++sub)
-                        tma_load_4d(st + sub * A_BYTES, &map_x, full_bar(s), kc * BK, kx - 1, h0 + sub * rows_per_sub + ky - 1, n);
-                    tma_load_2d(st + SUB * A_BYTES, &map_w, full_bar(s), kb * BK, 0);
+                for (int g = 0; g < groups; ++g, ++ia) {
+                    const int kx = g / kc_blocks, kc = g - kx * kc_blocks;
+                    const int sa = ia % SLABS;
+                    mbar_wait(a_empty(sa), ((ia / SLABS) & 1u) ^ 1u);
+                    mbar_expect_tx(a_full(sa), slab_bytes);
+                    tma_load_4d(base + sa * SLAB_BYTES, &map_x, a_full(sa), kc * BK, kx - 1, h0 - 1, n);
+                    for (int ky = 0; ky < 3; ++ky, ++ib) {
+                        const int sb = ib % B_STAGES;
+                        mbar_wait(b_empty(sb), ((ib / B_STAGES) & 1u) ^ 1u);
+                        mbar_expect_tx(b_full(sb), B_BYTES);
+                        tma_load_2d(b_base + sb * B_BYTES, &map_w, b_full(sb), ((ky * 3 + kx) * kc_blocks + kc) * BK, 0);
+                    }
                 }
             }
         }
@@ -134,44 +152,54 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     } else if (warp == 1) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            uint32_t it = 0, lt = 0;
+            uint32_t ia = 0, ib = 0, lt = 0;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
                 mbar_wait(tmem_empty_bar, (lt & 1u) ^ 1u);          // the epilogue has drained the previous tile (first passes)
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                for (int kb = 0; kb < num_k; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1u;
-                    mbar_wait(full_bar(s), ph);
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_addr = base + s * STAGE_BYTES, b_addr = a_addr + SUB * A_BYTES;
+                for (int g = 0; g < groups; ++g, ++ia) {
+                    const int sa = ia % SLABS;
+                    mbar_wait(a_full(sa), (ia / SLABS) & 1u);
+                    const uint32_t slab = base + sa * SLAB_BYTES;
+                    for (int ky = 0; ky < 3; ++ky, ++ib) {
+                        const int sb = ib % B_STAGES;
+                        mbar_wait(b_full(sb), (ib / B_STAGES) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_addr = b_base + sb * B_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / UMMA_K; ++k) {
-                        const uint64_t bd = make_desc(b_addr + k * UMMA_K * 2);
+                        for (int k = 0; k < BK / UMMA_K; ++k) {
+                            const uint64_t bd = make_desc(b_addr + k * UMMA_K * 2);
 #pragma unroll
-                        for (int sub = 0; sub < SUB; ++sub)
-                            umma_bf16(tmem_base + sub * BN, make_desc(a_addr + sub * A_BYTES + k * UMMA_K * 2), bd, IDESC, (kb | k) ? 1u : 0u);
+                            for (int sub = 0; sub < SUB; ++sub)   // vertical tap ky of accumulator `sub`: the slab, (sub * rows + ky) image rows down
+                                umma_bf16(tmem_base + sub * BN, make_desc(slab + (uint32_t)(sub * rows_per_sub + ky) * (uint32_t)row_bytes + k * UMMA_K * 2),
+                                          bd, IDESC, (g | ky | k) ? 1u : 0u);
+                        }
+                        umma_commit(b_empty(sb));
                     }
-                    umma_commit(empty_bar(s));
+                    umma_commit(a_empty(sa));
                 }
                 umma_commit(tmem_full_bar);
             }
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..5, TMEM lane quarter = warp % 4 =====
-        const int q = warp & 3;
-        uint32_t lt = 0;
+        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // Output path: a lane holds 32 consecutive channels of ONE pixel, so direct stores would touch 32 different lines per
+        // instruction (measured: the store wavefronts made the epilogue 13k cycles per tile).  Each 32 x 32 block goes through a
+        // 2 KB shared-memory buffer in TMA's 64-byte swizzle (conflict-free 16-byte writes) and leaves as one bulk tensor store.
+        const int q = warp & 3, half = (warp - 2) >> 2;
+        const uint32_t obuf = out_base + (uint32_t)(warp - 2) * (2 * OUT_BUF_BYTES);
+        uint32_t lt = 0, nst = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int n = tile / tiles_per_img, t_in = tile - n * tiles_per_img;
             mbar_wait(tmem_full_bar, lt & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
                 float st8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) st8[i] = 0.f;
 #pragma unroll
-                for (int sub = 0; sub < SUB; ++sub) {
+                for (int sub = 0; sub < SUB; ++sub, ++nst) {
                     uint32_t r[32];
                     const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(sub * BN + c);
                     asm volatile(
@@ -183,9 +211,12 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
                           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
+                    // the bulk store that used this buffer two blocks ago has finished reading it
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    __syncwarp();
+                    const uint32_t buf = obuf + (nst & 1u) * OUT_BUF_BYTES;
                     // this lane's output pixel: row 32q + lane of sub-tile `sub`; 32 consecutive channels c .. c+31
-                    __nv_bfloat16 *dst = y + ((size_t)tile * TILE_PIX + sub * BM + q * 32 + lane) * BN + c;
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint32_t pk[4];
@@ -195,7 +226,8 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                             const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
                             pk[t] = *reinterpret_cast<const uint32_t *>(&h);
                         }
-                        *reinterpret_cast<uint4 *>(dst + j) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+                        const uint32_t dst = buf + (uint32_t)lane * 64u + ((uint32_t)((j >> 3) ^ ((lane >> 1) & 3)) << 4);
+                        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
                         if (STATS) {
                             float s = 0.f, ss = 0.f;
 #pragma unroll
@@ -208,6 +240,13 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                             st8[(j >> 3) * 2 + 1] += ss;
                         }
                     }
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the TMA store
+                    __syncwarp();
+                    if (lane == 0) {
+                        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                     ::"l"(&map_y), "r"(buf), "r"(c), "r"(tile * TILE_PIX + sub * BM + q * 32) : "memory");
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                 }
                 if (STATS) {
                     const float tot = warp_sum8(st8, lane);
@@ -218,11 +257,12 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                     }
                 }
             }
-            // every TMEM read of this tile has completed: hand the accumulators back to the MMA warp
+            // every TMEM read of this warp's part of the tile has completed: hand the accumulators back to the MMA warp
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty_bar);
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // shared memory stays valid until the stores have read it
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -232,7 +272,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
 }
 
-// channel-last activation (N, H, W, C) bf16 as a 4-D tensor {C, W, H, N}; box = {64 channels, W, rows, 1}: 128 pixels x 128 bytes
+// channel-last activation (N, H, W, C) bf16 as a 4-D tensor {C, W, H, N}; box = {64 channels, W, rows, 1}: rows * W pixels x 128 bytes
 static bool make_act_map(CUtensorMap *map, const void *ptr, int N, int H, int W, int C, int rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
@@ -242,6 +282,18 @@ static bool make_act_map(CUtensorMap *map, const void *ptr, int N, int H, int W,
     const cuuint32_t estr[4] = {1, 1, 1, 1};
     return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// y as a row-major [pixels][256] bf16 matrix; box = 32 channels x 32 pixels in the 64-byte swizzle the epilogue writes
+static bool make_out_map(CUtensorMap *map, const void *ptr, long long rows) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)BN, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)BN * 2};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 }  // namespace conv
@@ -261,7 +313,8 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
     if (!x || !w_packed || !y) return GP_ERR_NULL;
     if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return GP_ERR_SHAPE;
     // 128 output pixels = whole image rows (W divides 128), a 256-pixel tile never straddles two images
-    if (Cout != BN || Cin % BK || W > 128 || BM % W || (H * W) % TILE_PIX || H % (SUB * (BM / W))) return GP_ERR_UNSUPPORTED;
+    // and a shift by one image row inside the slab stays aligned to the 1024-byte swizzle atom (W >= 8)
+    if (Cout != BN || Cin % BK || W > MAX_W || W < 8 || BM % W || (H * W) % TILE_PIX || H % (SUB * (BM / W))) return GP_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w_packed) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
     const long long tiles = (long long)N * (H * W / TILE_PIX);
     if (tiles >= (1ll << 31) / TILE_PIX) return GP_ERR_SHAPE;
@@ -276,14 +329,16 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
         cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     }
     const int sms = sms_of[dev];
-    CUtensorMap mx, mw;
-    if (!make_act_map(&mx, x, N, H, W, Cin, BM / W) || !make_map(&mw, w_packed, BN, 9 * Cin, BN)) return GP_ERR_UNSUPPORTED;
+    CUtensorMap mx, mw, my;
+    if (!make_act_map(&mx, x, N, H, W, Cin, TILE_PIX / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN) ||
+        !make_out_map(&my, y, tiles * TILE_PIX))
+        return GP_ERR_UNSUPPORTED;
     const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
     if (partial)
-        conv3x3_gn_kernel<true><<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, (__nv_bfloat16 *)y, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK);
+        conv3x3_gn_kernel<true><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
     else
-        conv3x3_gn_kernel<false><<<grid, THREADS, SMEM_BYTES, st>>>(mx, mw, (__nv_bfloat16 *)y, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK);
+        conv3x3_gn_kernel<false><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
     gp::g_launches += 1;
     return (int)cudaGetLastError();
 }

@@ -62,6 +62,10 @@ dcnv3_fwd_rows(const T *__restrict__ in, T *__restrict__ out, const __grid_const
     unsigned *s_unit = reinterpret_cast<unsigned *>(s_rec + t.n_ul * P);
     const uint32_t bar = (rows_smem_u32(s_unit + t.n_ul) + 7u) & ~7u;
 
+    // TMA moves 16-byte units: a box starts at the 16-byte boundary at or below the CTA's first value, `lead` values early
+    // (the box widths leave room for it)
+    constexpr int PER16 = 16 / (int)sizeof(T);
+    const int lead_off = (t.g0 * (P * 2)) & (PER16 - 1), lead_msk = (t.g0 * P) & (PER16 - 1);
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -69,9 +73,9 @@ dcnv3_fwd_rows(const T *__restrict__ in, T *__restrict__ out, const __grid_const
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
         const int row0 = t.b * p.Ho + t.oh0;
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(rows_smem_u32(s_off)), "l"(&map_off), "r"(bar), "r"(t.g0 * (P * 2)), "r"(t.ow0), "r"(row0) : "memory");
+                     ::"r"(rows_smem_u32(s_off)), "l"(&map_off), "r"(bar), "r"(t.g0 * (P * 2) - lead_off), "r"(t.ow0), "r"(row0) : "memory");
         asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-                     ::"r"(rows_smem_u32(s_msk)), "l"(&map_msk), "r"(bar), "r"(t.g0 * P), "r"(t.ow0), "r"(row0) : "memory");
+                     ::"r"(rows_smem_u32(s_msk)), "l"(&map_msk), "r"(bar), "r"(t.g0 * P - lead_msk), "r"(t.ow0), "r"(row0) : "memory");
     }
     __syncthreads();   // the barrier is initialised before anyone polls it
     asm volatile(
@@ -95,7 +99,7 @@ dcnv3_fwd_rows(const T *__restrict__ in, T *__restrict__ out, const __grid_const
             const int oh = t.oh0 + (pix >> p.lg_tw), ow = t.ow0 + (pix & (p.tile_w - 1));
             const int ul = gl * t.TP + pix;
             const bool live = e < t.n_ul && oh < p.Ho && ow < p.Wo;   // tile overhang: the sampling loop never visits the unit
-            const T *orow = s_off + (live ? pix * bw_off + gl * (P * 2) : 0), *mrow = s_msk + (live ? pix * bw_msk + gl * P : 0);
+            const T *orow = s_off + lead_off + (live ? pix * bw_off + gl * (P * 2) : 0), *mrow = s_msk + lead_msk + (live ? pix * bw_msk + gl * P : 0);
             const float p0_h_ = origin<float>(p.base_h + oh * p.sh, p.half_h, p.scale);
             const float p0_w_ = origin<float>(p.base_w + ow * p.sw, p.half_w, p.scale);
             float mx = 0.f, inv = 1.f;

@@ -205,11 +205,11 @@ def pack_conv3x3_weight(weight):
 
 
 def conv3x3_gn_supported(x, cout):
-    """Shapes the tcgen05 implicit-GEMM convolution takes: bf16 channel-last, Cout 256, Cin % 64 == 0, W | 128, H*W % 256 == 0."""
+    """Shapes the tcgen05 implicit-GEMM convolution takes: bf16 channel-last, Cout 256, Cin % 64 == 0, W in {8, 16, 32, 64}, H*W % 256 == 0."""
     if x.dim() != 4 or x.dtype != torch.bfloat16 or not x.is_cuda:
         return False
     N, H, W, C = x.shape
-    return cout == 256 and C % 64 == 0 and W <= 128 and 128 % W == 0 and (H * W) % 256 == 0 and H % (256 // W) == 0
+    return cout == 256 and C % 64 == 0 and 8 <= W <= 64 and 128 % W == 0 and (H * W) % 256 == 0 and H % (256 // W) == 0
 
 
 def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True):

@@ -209,7 +209,7 @@ int gp_groupnorm_finalize(const float *partial, float *stats, int N, int G, int 
  *   x (N,H,W,Cin) bf16 channel-last; w_packed [256][3][3][Cin] bf16 (= conv.weight.permute(0,2,3,1)); y (N,H,W,256) bf16.
  *   partial: NULL, or N * gp_conv3x3_gn_slabs(H,W) * 32 * 2 floats that receive the (sum, sum of squares) of the fp32
  *   accumulators per (image, 64-pixel slab, group of 8 channels) in the layout gp_groupnorm_finalize reads.
- * Supported: Cout == 256, Cin % 64 == 0, W in {16, 32, 64, 128} with H*W a multiple of 256 (whole 128-pixel row blocks).
+ * Supported: Cout == 256, Cin % 64 == 0, W in {8, 16, 32, 64} with H a multiple of 256/W (whole 256-pixel row blocks).
  * fp32 accumulation over K = 9*Cin in tensor memory; zero padding comes from TMA's out-of-bounds fill. */
 size_t gp_conv3x3_gn_slabs(int H, int W);
 int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout,

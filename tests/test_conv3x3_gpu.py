@@ -33,7 +33,7 @@ def _ref(x, w):
 
 # (N, H, W, Cin): the three decoder resolutions, more tiles than SMs (persistent loop, accumulator hand-back), other Cin
 SHAPES = [(1, 16, 16, 256), (3, 16, 16, 256), (2, 32, 32, 256), (2, 64, 64, 256), (40, 64, 64, 256), (5, 32, 32, 64),
-          (2, 16, 16, 1024), (1, 4, 64, 128), (2, 2, 128, 64)]
+          (2, 16, 16, 1024), (1, 4, 64, 128), (2, 32, 8, 64), (148 * 3 + 5, 16, 16, 64)]
 
 
 @pytest.mark.parametrize("N,H,W,Cin", SHAPES)
