@@ -311,7 +311,9 @@ def run_posenet(args, rank, world, dev, dist):
     B = total // world
     out = {"metric": "posenet_inference_rois_per_s", "unit": "RoIs/s", "batch_rois": total, "rois_per_rank": B,
            "scaling": "strong", "backbone": "ResNet-34 trunk + 1x1 neck (stand-in for timm ConvNeXt-B, needs the network)",
-           "weights": "random init (oracle.posenet.init_weights 'o1')", "gflop_per_roi": round(POSENET_GFLOP_PER_ROI, 2)}
+           "weights": "random init (oracle.posenet.init_weights 'o1')", "gflop_per_roi": round(POSENET_GFLOP_PER_ROI, 2),
+           "decoder_conv": "bf16: hand-written tcgen05 implicit GEMM with GroupNorm statistics in the epilogue (csrc/conv3x3_tc.cu); "
+                           "fp32 parity mode: cuDNN" if os.environ.get("GP_DECODER_CONV", "tc") == "tc" else "cuDNN (GP_DECODER_CONV=cudnn)"}
 
     def barrier():
         if world > 1:
@@ -448,7 +450,8 @@ def run_posenet(args, rank, world, dev, dist):
             peak = json.load(open(peaks_path)).get("bf16_tflops_sustained", 1383.2) if os.path.exists(peaks_path) else 1383.2
             entry["roofline"] = {"bound": "tensor", "achieved": entry["tflops"], "peak": peak * world, "unit": "TFLOP/s",
                                  "frac": round(entry["tflops"] / (peak * world), 4),
-                                 "note": "whole forward (library convs/GEMMs + our glue kernels) vs sustained bf16 GEMM peak"}
+                                 "note": "whole forward (hand-written tcgen05 decoder convs / PnP trunk / offset||mask GEMM, library backbone + 1x1 "
+                                         "GEMMs, our glue kernels) vs sustained bf16 GEMM peak"}
             out.update({"value": entry["value"], "value_bf16": entry["value"], "dtype": "bf16",
                         "dtype_note": "value / value_bf16: bf16 weights + activations, fp32 accumulation (stated tolerance: "
                                       "tests/test_posenet_gpu.py BF16_*); value_fp32: the 1e-4 parity mode (TF32 off)",
@@ -579,6 +582,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=8, help="RoI chunks of the pipelined host-buffer call (H2D | kernels | D2H)")
     ap.add_argument("--no-ceilings", action="store_true", help="skip the access-pattern micro-benchmark (tools/_bin/gather_rates)")
     ap.add_argument("--no-posenet", action="store_true", help="skip the PoseNet RoIs/s section")
     ap.add_argument("--posenet-rois", type=int, default=4096, help="RoIs per batch, sharded across the ranks (BASELINE configs[3])")
@@ -683,7 +687,7 @@ def main():
 
         def e2e_step():
             _lib.check(lib.gp_dcnv3_forward_backward_host(vp(hin), vp(hoff), vp(hm), vp(hgo), vp(hout), vp(hgi), vp(hgoff), vp(hgm),
-                                                          hoff.numel(), hm.numel(), ctypes.byref(d), dt_code, local_rank, 8),
+                                                          hoff.numel(), hm.numel(), ctypes.byref(d), dt_code, local_rank, args.e2e_chunks),
                        "fwd_bwd_host")
         e2e_steps = max(2, min(args.steps, 5))
         e2e_step()
@@ -703,7 +707,7 @@ def main():
             dist.all_reduce(pr, op=dist.ReduceOp.MIN)
         e2e = {"value": round((fwd_b + bwd_b) * world / t_e2e.item() / 1e9, 3), "unit": "GB/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(t_e2e.item() * 1e3, 3),
-               "steps": e2e_steps, "api": "gp_dcnv3_forward_backward_host (pinned host buffers, inputs uploaded once, 8 RoI chunks pipelined H2D | kernels | D2H)",
+               "steps": e2e_steps, "api": f"gp_dcnv3_forward_backward_host (pinned host buffers, inputs uploaded once, {args.e2e_chunks} RoI chunks pipelined H2D | kernels | D2H)",
                # the limiting resource, measured: each rank moves h2d bytes up and d2h bytes down per step over ITS PCIe link,
                # all ranks at once out of host memory; `pcie_probe` is the plain pinned-copy rate under the same concurrency
                "pcie": {"per_gpu_h2d_GBps": round(h2d / t_e2e.item() / 1e9, 1), "per_gpu_d2h_GBps": round(d2h / t_e2e.item() / 1e9, 1),
@@ -741,7 +745,7 @@ def main():
     roofline = {"bound": "hbm", "kernel": "dcnv3_bwd_tile (+ grad_input memset)", "achieved": round(ach, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes": bwd_b, "ms": round(ms_bwd, 4),
-                "fwd": {"kernel": "dcnv3_fwd_tile", "achieved": round(fwd_b / (ms_fwd * 1e-3) / 1e9, 1),
+                "fwd": {"kernel": "dcnv3_fwd_rows (offset / mask rows staged by TMA, 16-byte records)" if lib.gp_get_option(4) == 1 else "dcnv3_fwd_tile", "achieved": round(fwd_b / (ms_fwd * 1e-3) / 1e9, 1),
                         "frac": round(fwd_b / (ms_fwd * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": fwd_b, "ms": round(ms_fwd, 4)},
                 "fwd_bwd_frac": round((fwd_b + bwd_b) / ((ms_fwd + ms_bwd) * 1e-3) / 1e9 / peak, 4)}
 

@@ -18,12 +18,12 @@
 // ran at the L2 -> SM throughput cap: 64 KB of operands per 1024 tensor-pipe cycles; this one needs 48 KB per 1024).
 //
 // CTA tile = 256 pixels x 256 channels: two M128 x N256 accumulators = all 512 TMEM columns, so every 32 KB weight block
-// (256 rows x 64 K) that comes through shared memory feeds 2 x 4 MMAs.  Persistent CTAs (one per SM, 320 threads, warp-specialised):
+// (256 rows x 64 K) that comes through shared memory feeds 2 x 4 MMAs.  Persistent CTAs (one per SM, 576 threads, warp-specialised):
 //   warp 0     TMA producer: per (kx, kc) one activation slab into a ring of two, per tap one 2-D weight box into a ring of four
 //              32 KB stages; completion on mbarriers (expect_tx); runs ahead across tile boundaries
 //   warp 1     TMEM allocation (512 columns); one elected thread issues tcgen05.mma.cta_group::1.kind::f16 M128 N256 K16,
 //              tcgen05.commit releases the weight stage / the slab / publishes the accumulators
-//   warps 2-9  epilogue (two warps per TMEM lane quarter, 128 columns each): tcgen05.ld 32 lanes x 32 columns, GroupNorm partial
+//   warps 2-17 epilogue (four warps per TMEM lane quarter, 64 columns each): tcgen05.ld 32 lanes x 32 columns, GroupNorm partial
 //              sums of the fp32 values (transposing butterfly over the 32 rows of the warp: 9 shuffles per 4 groups), bf16 pack
 //              into a swizzled 2 KB staging block, one TMA bulk tensor store per block; the partials go out in the [n][slab][g][2] layout gn_finalize_kernel sums in a fixed order
 //              (no atomics: bit-reproducible)
@@ -41,10 +41,11 @@ constexpr int B_STAGES = 3;
 constexpr int MAX_W = 64;                        // widest image row: the slab holds 256/W + 2 rows of W pixels
 constexpr int SLAB_BYTES = (TILE_PIX + 2 * MAX_W) * BK * 2;   // 48 KB
 constexpr int SLABS = 2;
-constexpr int CONV_THREADS = 320;                // producer warp, MMA warp, 8 epilogue warps
+constexpr int EPI_WARPS = 16;                    // four per TMEM lane quarter, 64 accumulator columns each
+constexpr int CONV_THREADS = 64 + 32 * EPI_WARPS; // producer warp, MMA warp, epilogue warps
 constexpr int TMEM_COLS = SUB * BN;              // 512: the whole tensor memory of the SM
-constexpr int OUT_BUF_BYTES = 32 * 32 * 2;       // epilogue staging: 32 rows x 32 channels bf16 per TMA store, two buffers per warp
-constexpr int OUT_BYTES = 8 * 2 * OUT_BUF_BYTES; // 32 KB
+constexpr int OUT_BUF_BYTES = 32 * 32 * 2;       // epilogue staging: 32 rows x 32 channels bf16 per TMA store, one buffer per warp
+constexpr int OUT_BYTES = EPI_WARPS * OUT_BUF_BYTES;   // 32 KB
 constexpr size_t SMEM_BYTES = 1024 /*alignment slack*/ + (size_t)SLABS * SLAB_BYTES + (size_t)B_STAGES * B_BYTES + OUT_BYTES + 256 /*barriers*/;
 constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 constexpr int GN_GROUPS = 32;                    // GroupNorm(32, 256): 8 channels per group
@@ -112,7 +113,7 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
             mbar_init(a_empty(s), 1);
         }
         mbar_init(tmem_full_bar, 1);
-        mbar_init(tmem_empty_bar, 8);   // one arrival per epilogue warp
+        mbar_init(tmem_empty_bar, EPI_WARPS);   // one arrival per epilogue warp
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
@@ -182,19 +183,20 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ===== epilogue: warps 2..9; TMEM lane quarter = warp % 4, column half = (warp - 2) / 4 =====
+        // ===== epilogue: warps 2..17; TMEM lane quarter = warp % 4, column block = (warp - 2) / 4 =====
         // Output path: a lane holds 32 consecutive channels of ONE pixel, so direct stores would touch 32 different lines per
         // instruction (measured: the store wavefronts made the epilogue 13k cycles per tile).  Each 32 x 32 block goes through a
         // 2 KB shared-memory buffer in TMA's 64-byte swizzle (conflict-free 16-byte writes) and leaves as one bulk tensor store.
-        const int q = warp & 3, half = (warp - 2) >> 2;
-        const uint32_t obuf = out_base + (uint32_t)(warp - 2) * (2 * OUT_BUF_BYTES);
+        const int q = warp & 3, part = (warp - 2) >> 2;
+        constexpr int COLS = BN / (EPI_WARPS / 4);   // accumulator columns per warp
+        const uint32_t buf = out_base + (uint32_t)(warp - 2) * OUT_BUF_BYTES;
         uint32_t lt = 0, nst = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
             const int n = tile / tiles_per_img, t_in = tile - n * tiles_per_img;
             mbar_wait(tmem_full_bar, lt & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll 1
-            for (int c = half * (BN / 2); c < (half + 1) * (BN / 2); c += 32) {
+            for (int c = part * COLS; c < (part + 1) * COLS; c += 32) {
                 float st8[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) st8[i] = 0.f;
@@ -211,11 +213,10 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
                           "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
                           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
                         : "r"(taddr));
-                    // the bulk store that used this buffer two blocks ago has finished reading it
-                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                    // the bulk store of the previous block has finished reading the staging buffer
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                     __syncwarp();
-                    const uint32_t buf = obuf + (nst & 1u) * OUT_BUF_BYTES;
                     // this lane's output pixel: row 32q + lane of sub-tile `sub`; 32 consecutive channels c .. c+31
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {

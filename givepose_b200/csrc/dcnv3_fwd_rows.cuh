@@ -46,6 +46,8 @@ __host__ __device__ constexpr size_t fwd_rows_smem(int TP, int gs, int bw_off, i
            (size_t)TP * gs * 9 * 16 + (size_t)TP * gs * 4 + 16;
 }
 
+// 4 CTAs per SM (64 registers): budgets for 5 / 6 CTAs (48 / 40 registers, spills, less L1 next to the larger shared-memory
+// carve-out) were measured at 0.534 / 0.612 ms against 0.475 ms (profiles/r02_it6_fwd_rows_occupancy.json)
 template <typename T, int VEC, int L, bool SOFTMAX>
 __global__ void __launch_bounds__(kTileThreads, kTileMinBlocks)
 dcnv3_fwd_rows(const T *__restrict__ in, T *__restrict__ out, const __grid_constant__ CUtensorMap map_off,
