@@ -30,6 +30,33 @@ for dtype in (torch.float32, torch.bfloat16):
         F.dcnv3_forward(inp, off, m, *a, 256, 0, mask_is_logits=True)
         F.dcnv3_backward(inp, off, m, *a, gout, 256, 0)
 F.dcnv3_sample_index(off.float(), 2, 8, 11, 3, 3, 1, 1, 1, 1, 1, 1, 3, 1.0)
+# both forward kernels (GP_OPT_FWD_MODE 0: per-thread row reads, 1: TMA-staged rows) and every backward variant (0 scatter,
+# 1 split + binned grad_input, 2 fused in-SM aggregation) on a ragged, border-heavy shape; packed offset||logits rows
+from givepose_b200._lib import lib  # noqa: E402
+for dtype in (torch.float32, torch.bfloat16):
+    N, H, W, G, gc = 2, 13, 19, 4, 32
+    inp = r(N, H, W, G * gc).to(dev, dtype)
+    off = (r(N, H, W, G * 18) * 4).to(dev, dtype)
+    m = torch.softmax(r(N, H, W, G, 9), -1).reshape(N, H, W, G * 9).to(dev, dtype)
+    packed = torch.cat([off, m, torch.zeros(N, H, W, 4, device=dev, dtype=dtype)], -1).contiguous()
+    gout = r(N, H, W, G * gc).to(dev, dtype)
+    a = (3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0)
+    for fm in (0, 1):
+        lib.gp_set_option(4, fm)
+        F.dcnv3_forward(inp, off, m, *a, 256, 0)
+        F.dcnv3_forward_packed(inp, packed, *a, 256, 0)
+    for bm in (0, 1, 2):
+        lib.gp_set_option(0, bm)
+        F.dcnv3_backward(inp, off, m, *a, gout, 256, 0)
+    lib.gp_set_option(0, 0)
+# tcgen05 implicit-GEMM 3x3 convolution + GroupNorm statistics in the epilogue, TMA bulk-store epilogue; apply passes on its statistics
+for (N, H, W, Cin) in ((3, 16, 16, 64), (2, 32, 32, 128), (1, 64, 64, 64)):
+    xc = r(N, H, W, Cin).to(dev).bfloat16()
+    wp = ops.pack_conv3x3_weight((r(256, Cin, 3, 3) / (9 * Cin) ** 0.5).to(dev))
+    yc, st = ops.conv3x3_gn_bf16(xc, wp)
+    ops.groupnorm_apply(yc, st, torch.ones(256, device=dev), torch.zeros(256, device=dev), 32, 1e-5, "gelu", upsample2x=True)
+    ops.groupnorm_apply_conv1x1(yc, st, torch.ones(256, device=dev), torch.zeros(256, device=dev), r(3, 256).to(dev), r(3).to(dev))
+    ops.conv3x3_gn_bf16(xc, wp, stats=False)
 # glue kernels
 for dtype in (torch.float32, torch.bfloat16):
     x = r(3, 10, 12, 256).to(dev, dtype)
