@@ -27,7 +27,13 @@
 //              sums of the fp32 values (transposing butterfly over the 32 rows of the warp: 9 shuffles per 4 groups), bf16 pack
 //              into a swizzled 2 KB staging block, one TMA bulk tensor store per block; the partials go out in the [n][slab][g][2] layout gn_finalize_kernel sums in a fixed order
 //              (no atomics: bit-reproducible)
+#include <stdlib.h>
+
 #include "tc_common.cuh"
+
+#ifndef GP_CONV_PAIR_DEFAULT
+#define GP_CONV_PAIR_DEFAULT 1
+#endif
 
 namespace gp {
 namespace tc {
@@ -273,6 +279,259 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2, cluster of two CTAs on one TPC).  The pair shares one 256-pixel x 256-channel tile:
+// CTA r owns pixels [128 r, 128 r + 128) -- its own activation slab (128/W + 2 image rows) and HALF of every weight block (output
+// channels [128 r, +128), 16 KB) -- and the leader's single thread issues tcgen05.mma.cta_group::2 M256 N256 K16, which reads A
+// from each CTA's slab and the two B halves from both shared memories.  Per SM and K16 step that is 4 KB + 4 KB of operand reads
+// instead of 4 KB + 8 KB, and 26 KB instead of 48 KB of TMA fills per K64 block, so the shared-memory port (128 B/clk) no longer
+// limits the tensor pipe; and each CTA's accumulator is 128 lanes x 256 columns, so TWO accumulator sets fit in TMEM and the
+// epilogue of tile i overlaps the MMAs of tile i+1.
+//   full barriers live in the LEADER (its producer arms them for the bytes of both CTAs; the peer's TMA signals them through
+//   .cta_group::2), empty / accumulator-full barriers are local and receive the leader's multicast tcgen05.commit, the
+//   accumulator-empty barriers live in the leader and collect one arrival per epilogue warp of BOTH CTAs (remote arrive).
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace pair {
+constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;          // 16 KB: this CTA's half of a weight block
+constexpr int P_B_STAGES = 6;
+constexpr int P_SLAB_BYTES = (BM + 2 * MAX_W) * BK * 2;     // 32 KB: 128/W + 2 rows of W pixels
+constexpr int P_SLABS = 3;
+constexpr int ACCS = 2;                                   // accumulator sets (256 TMEM columns each)
+constexpr size_t P_SMEM_BYTES = 1024 + (size_t)P_SLABS * P_SLAB_BYTES + (size_t)P_B_STAGES * B_HALF_BYTES + OUT_BYTES + 512;
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t rank) {   // shared::cluster address of the same offset in CTA `rank`
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma2_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {   // arrives on `bar` at the same offset in BOTH CTAs of the pair
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+}   // namespace pair
+
+// n_tiles 256-pixel tiles, one per CTA pair and step; rows_per_sub = 128 / W; partial: [N][tiles_per_img * 8][32][2]
+template <bool STATS>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
+conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                       const __grid_constant__ CUtensorMap map_y, float *__restrict__ partial, int n_tiles, int tiles_per_img,
+                       int rows_per_sub, int kc_blocks, int row_bytes) {
+    using namespace pair;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t b_base = base + P_SLABS * P_SLAB_BYTES;
+    const uint32_t out_base = b_base + P_B_STAGES * B_HALF_BYTES;
+    const uint32_t bars = out_base + OUT_BYTES;
+    auto b_full = [&](int s) { return bars + 8u * s; };
+    auto b_empty = [&](int s) { return bars + 8u * (P_B_STAGES + s); };
+    auto a_full = [&](int s) { return bars + 8u * (2 * P_B_STAGES + s); };
+    auto a_empty = [&](int s) { return bars + 8u * (2 * P_B_STAGES + P_SLABS + s); };
+    auto tmem_full = [&](int a) { return bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + ACCS + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + 2 * ACCS);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int groups = 3 * kc_blocks;
+    const uint32_t slab_bytes = (uint32_t)(rows_per_sub + 2) * (uint32_t)row_bytes;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < P_B_STAGES; ++s) {
+            mbar_init(b_full(s), 1);
+            mbar_init(b_empty(s), 1);
+        }
+        for (int s = 0; s < P_SLABS; ++s) {
+            mbar_init(a_full(s), 1);
+            mbar_init(a_empty(s), 1);
+        }
+        for (int a = 0; a < ACCS; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 2 * EPI_WARPS);   // every epilogue warp of both CTAs
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    }
+    if (warp == 1) {   // one warp of EACH CTA takes part in the pair-wide allocation
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"((uint32_t)TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // both CTAs' barriers are initialised before any remote signal
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs): own slab + own half of the weight block, signalled on the LEADER's full barriers =====
+        if (lane == 0) {
+            uint32_t ia = 0, ib = 0;
+            for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+                const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * (SUB * rows_per_sub) + (int)rank * rows_per_sub;
+                for (int g = 0; g < groups; ++g, ++ia) {
+                    const int kx = g / kc_blocks, kc = g - kx * kc_blocks;
+                    const int sa = ia % P_SLABS;
+                    mbar_wait(a_empty(sa), ((ia / P_SLABS) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(a_full(sa), 2 * slab_bytes);
+                    tma2_load_4d(base + sa * P_SLAB_BYTES, &map_x, map_to_cta(a_full(sa), 0), kc * BK, kx - 1, h0 - 1, n);
+                    for (int ky = 0; ky < 3; ++ky, ++ib) {
+                        const int sb = ib % P_B_STAGES;
+                        mbar_wait(b_empty(sb), ((ib / P_B_STAGES) & 1u) ^ 1u);
+                        if (leader) mbar_expect_tx(b_full(sb), 2 * B_HALF_BYTES);
+                        tma2_load_2d(b_base + sb * B_HALF_BYTES, &map_w, map_to_cta(b_full(sb), 0), ((ky * 3 + kx) * kc_blocks + kc) * BK,
+                                     (int)rank * (BN / 2));
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: the leader's elected thread, for the pair =====
+        if (leader && lane == 0) {
+            uint32_t ia = 0, ib = 0, lt = 0;
+            for (int tile = pair_id; tile < n_tiles; tile += n_pairs, ++lt) {
+                const uint32_t acc = lt & 1u;
+                mbar_wait(tmem_empty(acc), ((lt >> 1) & 1u) ^ 1u);   // both CTAs have drained this accumulator set (first two pass)
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int g = 0; g < groups; ++g, ++ia) {
+                    const int sa = ia % P_SLABS;
+                    mbar_wait(a_full(sa), (ia / P_SLABS) & 1u);
+                    const uint32_t slab = base + sa * P_SLAB_BYTES;
+                    for (int ky = 0; ky < 3; ++ky, ++ib) {
+                        const int sb = ib % P_B_STAGES;
+                        mbar_wait(b_full(sb), (ib / P_B_STAGES) & 1u);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t b_addr = b_base + sb * B_HALF_BYTES;
+#pragma unroll
+                        for (int k = 0; k < BK / UMMA_K; ++k)
+                            umma2_bf16(tmem_d, make_desc(slab + (uint32_t)ky * (uint32_t)row_bytes + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2),
+                                       IDESC2, (g | ky | k) ? 1u : 0u);
+                        umma2_commit(b_empty(sb));
+                    }
+                    umma2_commit(a_empty(sa));
+                }
+                umma2_commit(tmem_full(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue (both CTAs): own 128 pixels; TMEM lane quarter = warp % 4, column block = (warp - 2) / 4 =====
+        const int q = warp & 3, part = (warp - 2) >> 2;
+        constexpr int COLS = BN / (EPI_WARPS / 4);
+        const uint32_t buf = out_base + (uint32_t)(warp - 2) * OUT_BUF_BYTES;
+        uint32_t lt = 0;
+        for (int tile = pair_id; tile < n_tiles; tile += n_pairs, ++lt) {
+            const int n = tile / tiles_per_img, t_in = tile - n * tiles_per_img;
+            const uint32_t acc = lt & 1u;
+            mbar_wait(tmem_full(acc), (lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = part * COLS; c < (part + 1) * COLS; c += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();
+                float st8[8];
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a = __uint_as_float(r[j + 2 * t]), b = __uint_as_float(r[j + 2 * t + 1]);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        pk[t] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    const uint32_t dst = buf + (uint32_t)lane * 64u + ((uint32_t)((j >> 3) ^ ((lane >> 1) & 3)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                    float s = 0.f, ss = 0.f;
+                    if (STATS) {
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            const float v = __uint_as_float(r[j + t]);
+                            s += v;
+                            ss = fmaf(v, v, ss);
+                        }
+                    }
+                    st8[(j >> 3) * 2] = s;
+                    st8[(j >> 3) * 2 + 1] = ss;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&map_y), "r"(buf), "r"(c), "r"(tile * TILE_PIX + (int)rank * BM + q * 32) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                if (STATS) {
+                    const float tot = warp_sum8(st8, lane);
+                    if ((lane & 3) == 0) {
+                        const int idx = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
+                        const int g = (c >> 3) + (idx >> 1);
+                        partial[(((size_t)n * (tiles_per_img * 8) + t_in * 8 + (int)rank * 4 + q) * GN_GROUPS + g) * 2 + (idx & 1)] = tot;
+                    }
+                }
+            }
+            // this warp's TMEM reads of the accumulator set are complete: tell the leader's MMA thread
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(tmem_empty(acc), 0));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();   // nobody frees tensor memory / exits while the peer may still signal or read
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)TMEM_COLS) : "memory");
+    }
+}
+
 // channel-last activation (N, H, W, C) bf16 as a 4-D tensor {C, W, H, N}; box = {64 channels, W, rows, 1}: rows * W pixels x 128 bytes
 static bool make_act_map(CUtensorMap *map, const void *ptr, int N, int H, int W, int C, int rows) {
     EncodeTiledFn fn = encode_fn();
@@ -301,11 +560,27 @@ static bool make_out_map(CUtensorMap *map, const void *ptr, long long rows) {
 }  // namespace tc
 }  // namespace gp
 
+// kernel variant: 0 = one CTA per tile (conv3x3_gn_kernel), 1 = CTA pair, tcgen05 cta_group::2 (conv3x3_gn_pair_kernel)
+static int g_conv_pair = -1;
+static int conv_pair_mode() {
+    if (g_conv_pair < 0) {
+        const char *e = getenv("GP_CONV_PAIR");
+        g_conv_pair = e ? (atoi(e) ? 1 : 0) : GP_CONV_PAIR_DEFAULT;
+    }
+    return g_conv_pair;
+}
+
 extern "C" {
+
+int gp_conv3x3_set_pair(int on) {
+    const int old = conv_pair_mode();
+    g_conv_pair = on ? 1 : 0;
+    return old;
+}
 
 size_t gp_conv3x3_gn_slabs(int H, int W) {
     if (H <= 0 || W <= 0 || (H * W) % gp::tc::conv::TILE_PIX) return 0;
-    return (size_t)(H * W / gp::tc::conv::TILE_PIX) * 4;
+    return (size_t)(H * W / gp::tc::conv::TILE_PIX) * (conv_pair_mode() ? 8 : 4);
 }
 
 int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream) {
@@ -326,20 +601,32 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
     if (!sms_of[dev]) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     }
     const int sms = sms_of[dev];
-    CUtensorMap mx, mw, my;
-    if (!make_act_map(&mx, x, N, H, W, Cin, TILE_PIX / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN) ||
-        !make_out_map(&my, y, tiles * TILE_PIX))
-        return GP_ERR_UNSUPPORTED;
-    const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
     cudaStream_t st = (cudaStream_t)stream;
-    if (partial)
-        conv3x3_gn_kernel<true><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
-    else
-        conv3x3_gn_kernel<false><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+    CUtensorMap mx, mw, my;
+    if (!make_out_map(&my, y, tiles * TILE_PIX)) return GP_ERR_UNSUPPORTED;
+    if (conv_pair_mode()) {
+        // CTA pair: each CTA loads the slab of its own 128 pixels and its half of the weight rows
+        if (!make_act_map(&mx, x, N, H, W, Cin, BM / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN / 2)) return GP_ERR_UNSUPPORTED;
+        const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
+        const unsigned grid = (unsigned)(2 * pairs);
+        if (partial)
+            conv3x3_gn_pair_kernel<true><<<grid, CONV_THREADS, pair::P_SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+        else
+            conv3x3_gn_pair_kernel<false><<<grid, CONV_THREADS, pair::P_SMEM_BYTES, st>>>(mx, mw, my, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+    } else {
+        if (!make_act_map(&mx, x, N, H, W, Cin, TILE_PIX / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN)) return GP_ERR_UNSUPPORTED;
+        const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
+        if (partial)
+            conv3x3_gn_kernel<true><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+        else
+            conv3x3_gn_kernel<false><<<grid, CONV_THREADS, SMEM_BYTES, st>>>(mx, mw, my, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+    }
     gp::g_launches += 1;
     return (int)cudaGetLastError();
 }

@@ -12,12 +12,16 @@ import torch.nn.functional as F
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(autouse=True)
-def _no_tf32():
-    old = torch.backends.cudnn.allow_tf32
+@pytest.fixture(autouse=True, params=[0, 1], ids=["one_cta", "cta_pair"])
+def _variant(request):
+    """Every test runs on both kernel variants: one CTA per tile, and the tcgen05 cta_group::2 CTA pair."""
+    from givepose_b200._lib import lib
+    old_tf32 = torch.backends.cudnn.allow_tf32
     torch.backends.cudnn.allow_tf32 = False
-    yield
-    torch.backends.cudnn.allow_tf32 = old
+    old = lib.gp_conv3x3_set_pair(request.param)
+    yield request.param
+    lib.gp_conv3x3_set_pair(old)
+    torch.backends.cudnn.allow_tf32 = old_tf32
 
 
 def _case(N, H, W, Cin, seed, scale=1.0):

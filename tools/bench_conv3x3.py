@@ -33,6 +33,10 @@ def main():
         wcl = w.contiguous(memory_format=torch.channels_last)
         gamma, beta = torch.ones(256, device="cuda"), torch.zeros(256, device="cuda")
         flops = 2.0 * N * R * R * 256 * 2304
+        from givepose_b200._lib import lib
+        lib.gp_conv3x3_set_pair(1)
+        t_pair = timeit(lambda: ops.conv3x3_gn_bf16(x, wp))
+        lib.gp_conv3x3_set_pair(0)
         t_tc = timeit(lambda: ops.conv3x3_gn_bf16(x, wp))
         t_tc_nostats = timeit(lambda: ops.conv3x3_gn_bf16(x, wp, stats=False))
         xn = x.permute(0, 3, 1, 2)
@@ -42,7 +46,7 @@ def main():
         _, st = ops.conv3x3_gn_bf16(x, wp)
         t_gn_apply = timeit(lambda: ops.groupnorm_apply(y, st, gamma, beta, 32, 1e-5, "gelu"))
         rec = {"N": N, "res": R, "tc_ms": round(t_tc, 4), "tc_nostats_ms": round(t_tc_nostats, 4), "cudnn_ms": round(t_cudnn, 4),
-               "tc_TFLOPs": round(flops / t_tc / 1e9, 1), "cudnn_TFLOPs": round(flops / t_cudnn / 1e9, 1),
+               "tc_TFLOPs": round(flops / t_tc / 1e9, 1), "pair_ms": round(t_pair, 4), "pair_TFLOPs": round(flops / t_pair / 1e9, 1), "cudnn_TFLOPs": round(flops / t_cudnn / 1e9, 1),
                "gn_stats_plus_apply_ms": round(t_gn_full, 4), "gn_apply_only_ms": round(t_gn_apply, 4),
                "convmodule_tc_ms": round(t_tc + t_gn_apply, 4), "convmodule_cudnn_ms": round(t_cudnn + t_gn_full, 4)}
         print(json.dumps(rec), flush=True)
