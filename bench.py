@@ -225,6 +225,25 @@ def pcie_probe(dev, barrier, mb=256):
         b.record()
         barrier()
         out[name + "_GBps"] = round(4 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
+    # both directions at once on two streams: what a pipelined H2D | kernels | D2H call can get out of the link per direction
+    h2, d2 = torch.empty(n, dtype=torch.uint8).pin_memory(), torch.empty(n, dtype=torch.uint8, device=dev)
+    s_up, s_dn = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    s_up.wait_event(a)
+    s_dn.wait_event(a)
+    with torch.cuda.stream(s_up):
+        for _ in range(4):
+            d.copy_(h, non_blocking=True)
+    with torch.cuda.stream(s_dn):
+        for _ in range(4):
+            h2.copy_(d2, non_blocking=True)
+    torch.cuda.current_stream(dev).wait_stream(s_up)
+    torch.cuda.current_stream(dev).wait_stream(s_dn)
+    b.record()
+    barrier()
+    out["duplex_GBps_per_direction"] = round(4 * n / (a.elapsed_time(b) * 1e-3) / 1e9, 1)
     return out
 
 
@@ -702,7 +721,7 @@ def main():
         nb = lambda x: x.numel() * x.element_size()
         h2d = nb(hin) + nb(hoff) + nb(hm) + nb(hgo)
         d2h = nb(hout) + nb(hgi) + nb(hgoff) + nb(hgm)
-        pr = torch.tensor([probe["h2d_GBps"], probe["d2h_GBps"]], device=dev, dtype=torch.float64)
+        pr = torch.tensor([probe["h2d_GBps"], probe["d2h_GBps"], probe["duplex_GBps_per_direction"]], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(pr, op=dist.ReduceOp.MIN)
         e2e = {"value": round((fwd_b + bwd_b) * world / t_e2e.item() / 1e9, 3), "unit": "GB/s",
@@ -711,9 +730,11 @@ def main():
                # the limiting resource, measured: each rank moves h2d bytes up and d2h bytes down per step over ITS PCIe link,
                # all ranks at once out of host memory; `pcie_probe` is the plain pinned-copy rate under the same concurrency
                "pcie": {"per_gpu_h2d_GBps": round(h2d / t_e2e.item() / 1e9, 1), "per_gpu_d2h_GBps": round(d2h / t_e2e.item() / 1e9, 1),
-                        "probe_min_over_ranks": {"h2d_GBps": round(pr[0].item(), 1), "d2h_GBps": round(pr[1].item(), 1), "concurrent_ranks": world},
+                        "probe_min_over_ranks": {"h2d_GBps": round(pr[0].item(), 1), "d2h_GBps": round(pr[1].item(), 1),
+                                                 "duplex_GBps_per_direction": round(pr[2].item(), 1), "concurrent_ranks": world},
                         "host_buffers": numa.info,
-                        "bound": "host: PCIe / host-memory bandwidth (1.5 GB up + 1.5 GB down per rank per step against 2 ms of kernels)"}}
+                        "bound": "PCIe, both directions busy: the pipelined call moves per_gpu_h2d/d2h GB/s against `duplex_GBps_per_direction` of the "
+                                 "plain pinned-copy probe (0.76 GB up + 0.76 GB down per rank per step against 1.9 ms of kernels)"}}
         lib.gp_host_cache_release()
 
     posenet = None
