@@ -13,7 +13,14 @@
 #include "tc_common.cuh"
 
 namespace gp {
+// The file is compiled twice (Makefile): GP_PART 1 = forward kernels + option / host-buffer entry points, GP_PART 2 = backward
+// kernels; 0 (default) = everything in one object.  Template instantiation of the sampling kernels dominates the build time.
+#ifndef GP_PART
+#define GP_PART 0
+#endif
+#if GP_PART != 2
 unsigned long long g_launches = 0;
+#endif
 
 struct Tuning {
     int tile_h = 8, tile_w = 8, gs = 2;   // measured best on B200 (profiles/r01_sweep.md)
@@ -25,7 +32,11 @@ struct Tuning {
     int fwd_mode = 1;
     bool init = false;
 };
-static Tuning g_tune;
+#if GP_PART != 2
+Tuning g_tune;
+#else
+extern Tuning g_tune;
+#endif
 
 static void init_tuning() {
     if (g_tune.init) return;
@@ -116,6 +127,7 @@ static size_t tile_smem(const KParams &p, bool softmax) {
 }
 static unsigned tile_grid(const KParams &p) { return (unsigned)((long long)p.N * p.tiles_y * p.tiles_x * p.gchunks); }
 
+#if GP_PART != 2
 template <typename T, int VEC, bool SOFTMAX>
 static void launch_fwd_tile(const void *in, const void *off, const void *msk, void *out, const KParams &p, int L,
                             cudaStream_t st) {
@@ -139,6 +151,8 @@ static void launch_fwd_tile(const void *in, const void *off, const void *msk, vo
     count_launch();
 }
 
+#endif
+#if GP_PART != 1
 template <typename T, int VEC, bool GIN>
 static void launch_bwd_tile(const void *in, const void *off, const void *msk, const void *gout, float *gin, void *goff,
                             void *gmsk, const KParams &p, int L, cudaStream_t st) {
@@ -287,6 +301,8 @@ static cudaError_t launch_bwd_fused(const void *in, const void *off, const void 
     return cudaErrorInvalidValue;
 }
 
+#endif
+#if GP_PART != 2
 template <typename T, bool SOFTMAX>
 static void launch_fwd_generic(const void *in, const void *off, const void *msk, void *out, const KParams &p,
                                cudaStream_t st) {
@@ -297,6 +313,8 @@ static void launch_fwd_generic(const void *in, const void *off, const void *msk,
     count_launch();
 }
 
+#endif
+#if GP_PART != 1
 template <typename T>
 static void launch_bwd_generic(const void *in, const void *off, const void *msk, const void *gout, void *gin_acc,
                                void *goff, void *gmsk, const KParams &p, cudaStream_t st) {
@@ -306,6 +324,8 @@ static void launch_bwd_generic(const void *in, const void *off, const void *msk,
     count_launch();
 }
 
+#endif
+#if GP_PART != 2
 // ---- forward with TMA-staged offset / mask rows (dcnv3_fwd_rows.cuh): 3x3 kernels ------------------------------------------
 // 3-D row tensor {row values, Wo, N*Ho} of `pitch` elements per pixel; box = {bw values, tile_w, tile_h}
 static bool make_rows_map(CUtensorMap *map, const void *base, int dtype, long long inner, long long pitch, const KParams &p, int bw) {
@@ -392,12 +412,14 @@ static int forward_impl(const void *in, const void *off, const void *msk, void *
     return (int)cudaGetLastError();
 }
 
+#endif
 }  // namespace gp
 
 using namespace gp;
 
 extern "C" {
 
+#if GP_PART != 2
 int gp_abi_version(void) { return GP_ABI_VERSION; }
 
 const char *gp_error_string(int code) {
@@ -473,6 +495,8 @@ int gp_dcnv3_forward_softmax_packed(const void *input, const void *offset_mask, 
     return forward_impl<true>(input, offset_mask, msk, out, desc, dtype, stream, pitch);
 }
 
+#endif
+#if GP_PART != 1
 size_t gp_dcnv3_backward_workspace(const gp_dcnv3_desc *desc, int dtype) {
     if (!desc || (dtype != GP_BF16 && dtype != GP_F16)) return 0;
     return (size_t)desc->N * desc->H * desc->W * desc->G * desc->gc * sizeof(float);
@@ -562,6 +586,8 @@ int gp_dcnv3_backward(const void *input, const void *offset, const void *mask, c
     return (int)ce;
 }
 
+#endif
+#if GP_PART != 2
 int gp_dcnv3_sample_index(const void *offset, int32_t *hw_low, uint8_t *flags, const gp_dcnv3_desc *desc, int dtype,
                           void *stream) {
     if (!offset || !hw_low || !flags) return GP_ERR_NULL;
@@ -795,4 +821,5 @@ int gp_dcnv3_forward_backward_host(const void *h_input, const void *h_offset, co
     return GP_OK;
 }
 
+#endif
 }  // extern "C"
