@@ -223,8 +223,9 @@ def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True):
     if tuple(w_packed.shape) != (Cout, 9 * C) or not conv3x3_gn_supported(x, Cout) or int(groups) != 32:
         raise RuntimeError(f"conv3x3_gn_bf16: unsupported shapes {tuple(x.shape)} x {tuple(w_packed.shape)} (groups {groups})")
     y = torch.empty((N, H, W, Cout), dtype=torch.bfloat16, device=x.device)
-    slabs = lib.gp_conv3x3_gn_slabs(H, W)
-    ws = torch.empty(N * 32 * 2 * (1 + slabs), dtype=torch.float32, device=x.device) if stats else None
+    slabs = lib.gp_conv3x3_gn_slabs(H, W)          # 4 (one CTA per tile) or 8 (CTA pair) partial rows per 256-pixel tile
+    room = max(slabs, 8 * (H * W // 256))          # sized for either kernel variant, whatever gp_conv3x3_set_pair says later
+    ws = torch.empty(N * 32 * 2 * (1 + room), dtype=torch.float32, device=x.device) if stats else None
     partial = ws[N * 32 * 2:] if stats else None
     with torch.cuda.device(x.device):
         check(lib.gp_conv3x3_gn_bf16(_vp(x), _vp(w_packed), _vp(y), _vp(partial) if stats else None, N, H, W, C, Cout, _stream(x)),
