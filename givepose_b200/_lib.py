@@ -57,6 +57,7 @@ EXPORTS = {
     "gp_groupnorm_act_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _I, _I, _I, _I, _VP]),
     "gp_groupnorm_act_conv1x1": (_I, [_VP, _VP, _VP, _SZ, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, ctypes.c_float, _I, _I, _I, _VP]),
     "gp_linear_bf16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, ctypes.c_float, _VP]),
+    "gp_linear_set_pair": (_I, [_I]),
     "gp_mhsa_tokens": (_I, [_VP, _VP, _I, _I, _I, _I, ctypes.c_float, _I, _VP]),
     "gp_stem_s2d_pack": (_I, [_VP, _VP, _I, _I, _I, _I, _VP]),
     "gp_upsample_bilinear2x": (_I, [_VP, _VP, _I, _I, _I, _I, _I, _VP]),

@@ -22,6 +22,8 @@
 // Rows / columns beyond M / N and the K tail are zero-filled by TMA on the way in and masked on the way out.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
+
 #include "tc_common.cuh"
 
 namespace gp {
@@ -222,6 +224,189 @@ linear_bf16_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_const
 }
 
 
+
+
+// ---------------------------------------------------------------------------------------------------------------------------
+// CTA-pair variant of the dense layer for large shapes (tcgen05 cta_group::2, cluster of two CTAs on one TPC): the pair owns a
+// 256 x 256 output tile; CTA r loads its own 128 rows of x and HALF of the weight rows (output columns [128 r, +128)) per K
+// step (16 + 16 KB per stage, ring of six), the leader's elected thread issues tcgen05.mma.cta_group::2 M256 N256 K16 (A from
+// each CTA's shared memory, the B halves from both), each CTA's accumulator is 128 lanes x 256 columns so two sets fit in TMEM
+// and the epilogue (bias + activation, bf16, 2 KB blocks in TMA's 64-byte swizzle, one bulk tensor store per block; rows / columns
+// beyond M / N are clipped by the tensor map) runs under the next tile's MMAs.  Barrier plumbing as in conv3x3_gn_pair_kernel.
+// ---------------------------------------------------------------------------------------------------------------------------
+namespace lpair {
+constexpr int BN2 = 256, HALF_BYTES = 128 * BK * 2;     // 16 KB: 128 rows x 64 K of x, or of w
+constexpr int STAGE_BYTES2 = 2 * HALF_BYTES, STAGES2 = 6;
+constexpr int EPI_WARPS2 = 16, THREADS2 = 64 + 32 * EPI_WARPS2;
+constexpr int OUT_BUF2 = 32 * 32 * 2, OUT_BYTES2 = EPI_WARPS2 * OUT_BUF2;
+constexpr size_t SMEM_BYTES2 = 1024 + (size_t)STAGES2 * STAGE_BYTES2 + OUT_BYTES2 + 512;
+constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN2 >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+}   // namespace lpair
+
+template <int ACT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(lpair::THREADS2, 1)
+linear_bf16_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
+                        const __grid_constant__ CUtensorMap map_y, const float *__restrict__ bias, int M, int N, int K, float slope) {
+    using namespace lpair;
+    using namespace pairops;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t out_base = base + STAGES2 * STAGE_BYTES2;
+    const uint32_t bars = out_base + OUT_BYTES2;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES2 + s); };
+    auto tmem_full = [&](int a) { return bars + 8u * (2 * STAGES2 + a); };
+    auto tmem_empty = [&](int a) { return bars + 8u * (2 * STAGES2 + 2 + a); };
+    const uint32_t tmem_slot = bars + 8u * (2 * STAGES2 + 4);
+    uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_rank();
+    const bool leader = rank == 0;
+    const int pair_id = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+    const int n_blocks = (N + BN2 - 1) / BN2, m_blocks = (M + 255) / 256;
+    const int tiles = n_blocks * m_blocks;
+    const int num_k = (K + BK - 1) / BK;
+
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(full_bar(s), 1);
+            mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tmem_full(a), 1);
+            mbar_init(tmem_empty(a), 2 * EPI_WARPS2);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_slot - base));
+
+    if (warp == 0) {
+        if (lane == 0) {   // ===== TMA producer (both CTAs) =====
+            uint32_t it = 0;
+            for (int tile = pair_id; tile < tiles; tile += n_pairs) {
+                const int m0 = (tile / n_blocks) * 256 + (int)rank * 128, n0 = (tile % n_blocks) * BN2 + (int)rank * 128;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES2;
+                    mbar_wait(empty_bar(s), ((it / STAGES2) & 1u) ^ 1u);
+                    if (leader) mbar_expect_tx(full_bar(s), 2 * STAGE_BYTES2);
+                    const uint32_t fb = map_to_cta(full_bar(s), 0);
+                    tma2_load_2d(base + s * STAGE_BYTES2, &map_x, fb, kb * BK, m0);
+                    tma2_load_2d(base + s * STAGE_BYTES2 + HALF_BYTES, &map_w, fb, kb * BK, n0);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (leader && lane == 0) {   // ===== MMA issuer (leader) =====
+            uint32_t it = 0, lt = 0;
+            for (int tile = pair_id; tile < tiles; tile += n_pairs, ++lt) {
+                const uint32_t acc = lt & 1u;
+                mbar_wait(tmem_empty(acc), ((lt >> 1) & 1u) ^ 1u);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t tmem_d = tmem_base + acc * BN2;
+                for (int kb = 0; kb < num_k; ++kb, ++it) {
+                    const int s = it % STAGES2;
+                    mbar_wait(full_bar(s), (it / STAGES2) & 1u);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_addr = base + s * STAGE_BYTES2, b_addr = a_addr + HALF_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / UMMA_K; ++k)
+                        umma2_bf16(tmem_d, make_desc(a_addr + k * UMMA_K * 2), make_desc(b_addr + k * UMMA_K * 2), IDESC2, (kb | k) ? 1u : 0u);
+                    umma2_commit(empty_bar(s));
+                }
+                umma2_commit(tmem_full(acc));
+            }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue (both CTAs): own 128 rows; TMEM lane quarter = warp % 4, 64-column block = (warp - 2) / 4 =====
+        const int q = warp & 3, part = (warp - 2) >> 2;
+        const uint32_t buf = out_base + (uint32_t)(warp - 2) * OUT_BUF2;
+        uint32_t lt = 0;
+        for (int tile = pair_id; tile < tiles; tile += n_pairs, ++lt) {
+            const int m0 = (tile / n_blocks) * 256 + (int)rank * 128, n0 = (tile % n_blocks) * BN2;
+            const uint32_t acc = lt & 1u;
+            mbar_wait(tmem_full(acc), (lt >> 1) & 1u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int c = part * 64; c < part * 64 + 64; c += 32) {
+                uint32_t r[32];
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN2 + c);
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                    "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                      "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+                      "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+                      "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                    : "r"(taddr));
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                __syncwarp();
+                const int col0 = n0 + c;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float bv[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) bv[t] = col0 + j + t < N ? __ldg(bias + col0 + j + t) : 0.f;
+                    uint32_t pk[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float a = activate<ACT>(__uint_as_float(r[j + 2 * t]) + bv[2 * t], slope);
+                        const float b = activate<ACT>(__uint_as_float(r[j + 2 * t + 1]) + bv[2 * t + 1], slope);
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                        pk[t] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    const uint32_t dst = buf + (uint32_t)lane * 64u + ((uint32_t)((j >> 3) ^ ((lane >> 1) & 3)) << 4);
+                    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(pk[0]), "r"(pk[1]), "r"(pk[2]), "r"(pk[3]) : "memory");
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0 && col0 < N && m0 + q * 32 < M) {   // the tensor map clips rows >= M / columns >= N of the block
+                    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                                 ::"l"(&map_y), "r"(buf), "r"(col0), "r"(m0 + q * 32) : "memory");
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(tmem_empty(acc), 0));
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// y as a row-major [M][N] bf16 matrix; box = 32 columns x 32 rows in the 64-byte swizzle the pair kernel's epilogue writes
+static bool make_out_map2(CUtensorMap *map, const void *ptr, int M, int N) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+    const cuuint64_t strides[1] = {(cuuint64_t)N * 2};
+    const cuuint32_t box[2] = {32, 32};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
 
 // ---------------------------------------------------------------------------------------------------------------------------
 // Stem of the stand-in backbone as an implicit GEMM on the tensor cores: the 7x7/2 convolution runs as a 4x4/1 convolution
@@ -508,6 +693,31 @@ static int launch_linear(const void *x, const void *w, const float *bias, void *
     return (int)cudaGetLastError();
 }
 
+template <int ACT>
+static int launch_linear_pair(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, float slope, cudaStream_t st) {
+    using namespace gp::tc;
+    using namespace gp::tc::lpair;
+    static int sms_of[kMaxDevices] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= kMaxDevices) return GP_ERR_UNSUPPORTED;
+    if (!sms_of[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(linear_bf16_pair_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES2);
+        if (e != cudaSuccess) return (int)e;
+        cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
+    }
+    CUtensorMap mx, mw, my;
+    if (!make_map(&mx, x, M, K, 128) || !make_map(&mw, w, N, K, 128) || !make_out_map2(&my, y, M, N)) return GP_ERR_UNSUPPORTED;
+    const long long tiles = (long long)((N + 255) / 256) * ((M + 255) / 256);
+    const long long pairs = tiles < sms_of[dev] / 2 ? tiles : sms_of[dev] / 2;
+    linear_bf16_pair_kernel<ACT><<<(unsigned)(2 * pairs), THREADS2, SMEM_BYTES2, st>>>(mx, mw, my, bias, M, N, K, slope);
+    gp::g_launches += 1;
+    return (int)cudaGetLastError();
+}
+
+// kernel choice for large shapes: -1 = automatic (CTA pair when the 256 x 256 tiles fill the machine), 0 = never, 1 = whenever legal
+static int g_linear_pair = -1;
+
 template <int BN>
 static int launch_linear_act(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
                              cudaStream_t st) {
@@ -517,6 +727,12 @@ static int launch_linear_act(const void *x, const void *w, const float *bias, vo
     return launch_linear<BN, ACT_NONE>(x, w, bias, y, M, N, K, slope, st);
 }
 
+extern "C" int gp_linear_set_pair(int mode) {   // -1 / 2 automatic, 0 never, 1 whenever legal; returns the previous mode
+    const int old = g_linear_pair < 0 ? 2 : g_linear_pair;
+    g_linear_pair = mode < 0 ? 2 : mode;
+    return old;
+}
+
 extern "C" int gp_linear_bf16(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
                               void *stream) {
     if (!x || !w || !bias || !y) return GP_ERR_NULL;
@@ -524,6 +740,18 @@ extern "C" int gp_linear_bf16(const void *x, const void *w, const float *bias, v
     if (act < 0 || act > 2 || (act == 1 && !(slope >= 0.f && slope <= 1.f))) return GP_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(y)) & 15u) return GP_ERR_ALIGN;
     if (M == 0) return GP_OK;
+    // CTA pairs (cta_group::2, 256 x 256 tiles) for the large layers: N a multiple of 8 (16-byte output rows for the TMA store)
+    {
+        if (g_linear_pair < 0) { const char *e = getenv("GP_LINEAR_PAIR"); g_linear_pair = e ? atoi(e) : 2; }
+        const long long t256 = (long long)((N + 255) / 256) * ((M + 255) / 256);
+        const bool legal = N % 8 == 0 && M >= 128 && N >= 128;
+        if (legal && (g_linear_pair == 1 || (g_linear_pair == 2 && t256 >= 64 && K >= 512))) {
+            cudaStream_t st = (cudaStream_t)stream;
+            if (act == gp::tc::ACT_LRELU) return launch_linear_pair<gp::tc::ACT_LRELU>(x, w, bias, y, M, N, K, slope, st);
+            if (act == gp::tc::ACT_RELU) return launch_linear_pair<gp::tc::ACT_RELU>(x, w, bias, y, M, N, K, slope, st);
+            return launch_linear_pair<gp::tc::ACT_NONE>(x, w, bias, y, M, N, K, slope, st);
+        }
+    }
     // 128 x 256 tiles when there are enough of them to fill the machine: x is read once per 256 output columns, and a
     // K16 step reads 12 KB of operands per 128 tensor-pipe cycles instead of 8 KB per 64 (shared-memory bound at N = 128)
     const long long tiles256 = (long long)((N + 255) / 256) * ((M + 127) / 128);

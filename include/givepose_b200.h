@@ -251,6 +251,10 @@ int gp_resize_linear_u8_normalize(const uint8_t *images, int n_images, int H, in
  * K % 8 == 0 (16-byte row pitch); any M, N (tails are masked).  TMA operand loads, 3-stage mbarrier ring, two CTAs per SM. */
 int gp_linear_bf16(const void *x, const void *w, const float *bias, void *y, int M, int N, int K, int act, float slope,
                    void *stream);
+/* Kernel choice of gp_linear_bf16 for large shapes: 2 (default) = CTA pairs (tcgen05 cta_group::2, 256 x 256 tiles, two accumulator
+ * sets) when at least 64 such tiles exist and K >= 512, 0 = always one CTA per tile, 1 = CTA pairs whenever legal (N % 8 == 0,
+ * M, N >= 128).  Returns the previous mode; GP_LINEAR_PAIR in the environment sets the initial one. */
+int gp_linear_set_pair(int mode);
 
 /* Multi-head self-attention over the 64 patch tokens of MAPTransformerEncoer (attention_pnp_net.py:126-157, the
  * `--nocsmap_encoder=att` alternative to MAPEncoder; timm 0.9.6 Attention.forward): out = softmax(q k^T * scale) v per head.

@@ -14,12 +14,22 @@ def rel(a, b):
     return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
 
 
-SHAPES = [(128, 128, 64), (256, 256, 256), (677, 108, 256), (300, 2048, 1024), (128, 136, 8192), (5, 8, 72), (1000, 256, 1024)]
+SHAPES = [(128, 128, 64), (256, 256, 256), (677, 108, 256), (300, 2048, 1024), (128, 136, 8192), (5, 8, 72), (1000, 256, 1024),
+          (4096, 2048, 512), (1300, 1032, 1088), (257, 264, 72)]
+
+
+@pytest.fixture(params=[0, 1], ids=["one_cta", "cta_pair"])
+def pair_mode(request):
+    """0: always one CTA per tile; 1: the tcgen05 cta_group::2 CTA-pair kernel whenever the shape is legal for it."""
+    from givepose_b200._lib import lib
+    old = lib.gp_linear_set_pair(request.param)
+    yield request.param
+    lib.gp_linear_set_pair(old)
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)
 @pytest.mark.parametrize("act", ["none", "lrelu", "relu"])
-def test_linear_bf16_matches_torch(M, N, K, act):
+def test_linear_bf16_matches_torch(M, N, K, act, pair_mode):
     from givepose_b200 import ops
     g = torch.Generator().manual_seed(M + N + K)
     x = torch.randn(M, K, generator=g).bfloat16()
