@@ -14,6 +14,9 @@
 //   mode 4  shared-memory reads only: the LDS patterns the kernels use (16-byte broadcast records, 128-byte rows)
 //   mode 5  the backward's scatter alone: 36 red.global.add.v4.f32 line reductions per unit to the same addresses (fp32)
 //   mode 6  gather + scatter: 36 line gathers AND 36 line reductions per unit (the one-pass backward's memory pattern)
+//   mode 7  scatter, best locality: the 36 reductions of a unit all go to ONE line (its own output pixel)
+//   mode 8  scatter, no locality: 36 reductions per unit to pseudo-random lines of the whole 268 MB image tensor
+//           (7 and 8 bracket mode 5: does the chip's reduction rate depend on WHERE the lines are?)
 // Output: ms per launch, units/clk/SM, and for modes 0-3 the bytes-gathered rate.  The forward can not be faster than
 // mode 0 (fp32) / mode 1-2 (bf16) with the same decomposition; the figure bench.py quotes as `l1_gather_floor_ms`.
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/_bin/gather_rates tools/micro/gather_rates.cu
@@ -90,7 +93,12 @@ gather(const void *__restrict__ in, const int *__restrict__ offs, void *__restri
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 const char *ptr = in_g + (long long)oo[k] * (C * EB);
-                if (MODE == 5 || MODE == 6) {   // `out` is the fp32 accumulation image (same shape as `in`)
+                if (MODE == 7) {
+                    red_v4(reinterpret_cast<float *>((char *)out + (q * C + g * GC) * 4 + cl * 16), 1.f, 1.f, 1.f, 1.f);
+                } else if (MODE == 8) {
+                    const uint32_t line = hash32((uint32_t)u * 36u + pt * 4 + k) % (uint32_t)(N * H * W * G);
+                    red_v4(reinterpret_cast<float *>((char *)out + (size_t)line * 128 + cl * 16), 1.f, 1.f, 1.f, 1.f);
+                } else if (MODE == 5 || MODE == 6) {   // `out` is the fp32 accumulation image (same shape as `in`)
                     float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
                     if (MODE == 6) v = __ldg(reinterpret_cast<const float4 *>(ptr));
                     red_v4(reinterpret_cast<float *>((char *)out + (ptr - (const char *)in)), v.x, v.y, v.z, v.w);
@@ -104,7 +112,7 @@ gather(const void *__restrict__ in, const int *__restrict__ offs, void *__restri
             }
         }
         char *o_ptr = (char *)out + (q * C + g * GC) * EB + cl * LB;
-        if (MODE == 5 || MODE == 6) continue;
+        if (MODE >= 5) continue;
         if (LB == 16) *reinterpret_cast<float4 *>(o_ptr) = make_float4(acc[0], acc[1], acc[2], acc[3]);
         else *reinterpret_cast<float2 *>(o_ptr) = make_float2(acc[0], acc[1]);
     }
@@ -181,6 +189,10 @@ int main() {
         run<2>("16-bit, 4 lanes x 16 B (half lines)", in, offs, out, dist);
         run<5>("fp32 scatter only: 36 red.v4 lines per unit", in, offs, out, dist);
         run<6>("fp32 gather + scatter: 36 + 36 lines per unit", in, offs, out, dist);
+        if (dist == 0) {
+            run<7>("fp32 scatter, 36 reductions to ONE line per unit", in, offs, out, dist);
+            run<8>("fp32 scatter, 36 reductions to random lines", in, offs, out, dist);
+        }
     }
     run<3>("fp32, offsets from registers (no record reads)", in, offs, out, 0);
     run_lds<0>("LDS.128, 4 distinct 16 B records per warp (8-lane broadcast)", sink);
