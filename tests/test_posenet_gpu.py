@@ -706,3 +706,24 @@ def test_posenet_bf16_64_rois_against_fp32(OP):
     assert ang.median() < BF16_ROT_MEDIAN_DEG, ang.median()
     assert int(well.sum()) >= 16 and ang[well].max() < BF16_ROT_WELL_DEG, sorted(ang[well].tolist())[-5:]
     assert bool((ang <= bound).all()), [(float(x_), float(y_), float(c_)) for x_, y_, c_ in zip(ang, bound, cond) if x_ > y_]
+
+
+def test_posenet_bf16_pnp_trunk_on_the_cta_pair_gemm(OP):
+    """The PnP trunk's fc1||fc1_z runs on the CTA-pair dense layer (tcgen05 cta_group::2) for large batches (>= 2048 RoIs by
+    default).  Forced on here for a 128-RoI batch and compared with the one-CTA kernel: same operands, fp32 accumulation in a
+    different order, one bf16 rounding -> the raw 6-D rotation / translation outputs agree to 1e-2 of their max."""
+    from givepose_b200._lib import lib
+    data = OP.make_inputs(128, seed=5)
+    _, net = build(OP, "o1", precision="bf16")
+    outs = []
+    old = lib.gp_linear_set_pair(0)
+    try:
+        for mode in (0, 1):
+            lib.gp_linear_set_pair(mode)
+            tap = _tap_rot6(net)
+            with torch.no_grad():
+                o = net(data, "cuda")
+            outs.append((tap["rot6"], o["trans"].double().cpu()))
+    finally:
+        lib.gp_linear_set_pair(old)
+    assert rel(outs[1][0], outs[0][0]) < 1e-2 and rel(outs[1][1], outs[0][1]) < 1e-2, (rel(outs[1][0], outs[0][0]), rel(outs[1][1], outs[0][1]))
