@@ -52,6 +52,7 @@ EXPORTS = {
     "gp_groupnorm_finalize": (_I, [_VP, _VP, _I, _I, _I, ctypes.c_longlong, ctypes.c_float, _VP]),
     "gp_conv3x3_gn_slabs": (_SZ, [_I, _I]),
     "gp_conv3x3_set_pair": (_I, [_I]),
+    "gp_conv3x3_gn_bf16_fused_in": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "gp_conv3x3_gn_bf16": (_I, [_VP, _VP, _VP, _VP, _I, _I, _I, _I, _I, _VP]),
     "gp_groupnorm_backward_workspace_floats": (_SZ, [_I, _I, _I, _I, _I]),
     "gp_groupnorm_act_backward": (_I, [_VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _I, _I, _I, _I, _I, _I, _I, _VP]),

@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "tc_common.cuh"
+#include "gelu_fast.cuh"
 
 #ifndef GP_CONV_PAIR_DEFAULT
 #define GP_CONV_PAIR_DEFAULT 1
@@ -305,12 +306,26 @@ using namespace gp::tc::pairops;
 }   // namespace pair
 
 // n_tiles 256-pixel tiles, one per CTA pair and step; rows_per_sub = 128 / W; partial: [N][tiles_per_img * 8][32][2]
-template <bool STATS>
+//
+// XFORM: the input x is the RAW output of the previous ConvModule's convolution, and this kernel applies that module's
+// GroupNorm + GELU (conv_module.py order conv -> norm -> act) to the operand ON ITS WAY to the tensor core, so the apply pass
+// over the previous activation (one read + one write of the whole tensor at the HBM rate) disappears: eight transform warps
+// per CTA wait for a slab to land, rewrite it in place -- z = bf16(gelu(x * sc + sh)) with (sc, sh) folded from the producer
+// layer's (mean, rstd), gamma, beta exactly as gn_apply_kernel does, so the operand bits are those the unfused pipeline would
+// have read -- skip the positions TMA zero-filled (the convolution pads the ACTIVATED tensor with zeros), make the writes
+// visible to the async proxy and arrive on the leader's `ready` barrier the MMA thread waits on.  A thread's 16-byte slots all
+// hold the same channel octet (the slab's 128-byte swizzle depends on the pixel row mod 8 and a thread's rows are 32 apart), so
+// its eight (sc, sh) pairs are loaded once per slab.  Each slab is one horizontal tap of one 64-channel block: an element is
+// transformed three times per tile instead of once -- ALU work the MMA-bound kernel has issue slots for.
+template <bool STATS, bool XFORM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS, 1)
 conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                        const __grid_constant__ CUtensorMap map_y, float *__restrict__ partial, int n_tiles, int tiles_per_img,
-                       int rows_per_sub, int kc_blocks, int row_bytes) {
+                       int rows_per_sub, int kc_blocks, int row_bytes, const float *__restrict__ in_stats /*[N][32][2]*/,
+                       const float *__restrict__ in_gamma, const float *__restrict__ in_beta, int H, int lgW) {
     using namespace pair;
+    constexpr int NEPI = XFORM ? 8 : EPI_WARPS;     // epilogue warps (XFORM: warps 2..9, transform warps 10..17)
+    constexpr int NXF = 8;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t b_base = base + P_SLABS * P_SLAB_BYTES;
@@ -322,7 +337,8 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
     auto a_empty = [&](int s) { return bars + 8u * (2 * P_B_STAGES + P_SLABS + s); };
     auto tmem_full = [&](int a) { return bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + a); };
     auto tmem_empty = [&](int a) { return bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + ACCS + a); };
-    const uint32_t tmem_slot = bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + 2 * ACCS);
+    auto a_ready = [&](int s) { return bars + 8u * (2 * P_B_STAGES + 2 * P_SLABS + 2 * ACCS + s); };   // XFORM: leader, 2 x NXF arrivals
+    const uint32_t tmem_slot = bars + 8u * (2 * P_B_STAGES + 3 * P_SLABS + 2 * ACCS);
     uint8_t *smem_gen = smem_raw + (base - smem_u32(smem_raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -340,10 +356,11 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
         for (int s = 0; s < P_SLABS; ++s) {
             mbar_init(a_full(s), 1);
             mbar_init(a_empty(s), 1);
+            mbar_init(a_ready(s), 2 * NXF);            // XFORM: every transform warp of both CTAs
         }
         for (int a = 0; a < ACCS; ++a) {
             mbar_init(tmem_full(a), 1);
-            mbar_init(tmem_empty(a), 2 * EPI_WARPS);   // every epilogue warp of both CTAs
+            mbar_init(tmem_empty(a), 2 * NEPI);        // every epilogue warp of both CTAs
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
@@ -370,8 +387,13 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                     const int kx = g / kc_blocks, kc = g - kx * kc_blocks;
                     const int sa = ia % P_SLABS;
                     mbar_wait(a_empty(sa), ((ia / P_SLABS) & 1u) ^ 1u);
-                    if (leader) mbar_expect_tx(a_full(sa), 2 * slab_bytes);
-                    tma2_load_4d(base + sa * P_SLAB_BYTES, &map_x, map_to_cta(a_full(sa), 0), kc * BK, kx - 1, h0 - 1, n);
+                    if (XFORM) {   // the slab lands on this CTA's own barrier: its transform warps take it from there
+                        mbar_expect_tx(a_full(sa), slab_bytes);
+                        tma_load_4d(base + sa * P_SLAB_BYTES, &map_x, a_full(sa), kc * BK, kx - 1, h0 - 1, n);
+                    } else {
+                        if (leader) mbar_expect_tx(a_full(sa), 2 * slab_bytes);
+                        tma2_load_4d(base + sa * P_SLAB_BYTES, &map_x, map_to_cta(a_full(sa), 0), kc * BK, kx - 1, h0 - 1, n);
+                    }
                     for (int ky = 0; ky < 3; ++ky, ++ib) {
                         const int sb = ib % P_B_STAGES;
                         mbar_wait(b_empty(sb), ((ib / P_B_STAGES) & 1u) ^ 1u);
@@ -394,7 +416,7 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 const uint32_t tmem_d = tmem_base + acc * BN;
                 for (int g = 0; g < groups; ++g, ++ia) {
                     const int sa = ia % P_SLABS;
-                    mbar_wait(a_full(sa), (ia / P_SLABS) & 1u);
+                    mbar_wait(XFORM ? a_ready(sa) : a_full(sa), (ia / P_SLABS) & 1u);
                     const uint32_t slab = base + sa * P_SLAB_BYTES;
                     for (int ky = 0; ky < 3; ++ky, ++ib) {
                         const int sb = ib % P_B_STAGES;
@@ -413,10 +435,61 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
             }
         }
         __syncwarp();
+    } else if (XFORM && warp >= 2 + NEPI) {
+        // ===== operand transform (both CTAs): GroupNorm + GELU of the producer layer, in place, slab by slab =====
+        const int tx = threadIdx.x - 32 * (2 + NEPI);            // 0 .. 255
+        const int j = tx & 7, jl = j ^ ((tx >> 3) & 7);          // physical 16-byte slot in the row / the channel octet it holds
+        const int W = 1 << lgW, cpg = kc_blocks * BK / GN_GROUPS;  // channels per group of the producer's GroupNorm(32)
+        const int npix = (rows_per_sub + 2) << lgW;
+        uint8_t *slab0 = smem_gen;                                 // generic pointer to the slab ring
+        uint32_t ia = 0;
+        for (int tile = pair_id; tile < n_tiles; tile += n_pairs) {
+            const int n = tile / tiles_per_img, h0 = (tile - n * tiles_per_img) * (SUB * rows_per_sub) + (int)rank * rows_per_sub;
+            for (int g = 0; g < groups; ++g, ++ia) {
+                const int kx = g / kc_blocks, kc = g - kx * kc_blocks;
+                const int sa = ia % P_SLABS;
+                // this thread's eight (scale, shift) pairs: channels c0 .. c0+7 of image n (one GroupNorm group when cpg % 8 == 0)
+                const int c0 = kc * BK + jl * 8;
+                const float mean = __ldg(in_stats + ((size_t)n * GN_GROUPS + c0 / cpg) * 2), rstd = __ldg(in_stats + ((size_t)n * GN_GROUPS + c0 / cpg) * 2 + 1);
+                float sc[8], sh[8];
+                {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4 *>(in_gamma + c0)), g1 = __ldg(reinterpret_cast<const float4 *>(in_gamma + c0 + 4));
+                    const float4 b0 = __ldg(reinterpret_cast<const float4 *>(in_beta + c0)), b1 = __ldg(reinterpret_cast<const float4 *>(in_beta + c0 + 4));
+                    const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {   // gn_fold: y = x * sc + sh
+                        sc[t] = rstd * gm[t];
+                        sh[t] = bt[t] - mean * sc[t];
+                    }
+                }
+                mbar_wait(a_full(sa), (ia / P_SLABS) & 1u);                  // the slab has landed (TMA, async proxy)
+                uint8_t *slab = slab0 + sa * P_SLAB_BYTES;
+                for (int q = tx; q < npix * 8; q += 32 * NXF) {
+                    const int r = q >> 3, row = r >> lgW, col = r & (W - 1);
+                    const int ih = h0 - 1 + row, iw = col + kx - 1;
+                    if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;      // zero padding of the ACTIVATED tensor: leave TMA's zeros
+                    uint4 *cell = reinterpret_cast<uint4 *>(slab + (size_t)r * 128 + j * 16);
+                    const uint4 v = *cell;
+                    const uint32_t wds[4] = {v.x, v.y, v.z, v.w};
+                    uint32_t o[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) {
+                        const float x0 = __uint_as_float(wds[t] << 16), x1 = __uint_as_float(wds[t] & 0xffff0000u);
+                        const float z0 = gelu_fast16(fmaf(x0, sc[2 * t], sh[2 * t])), z1 = gelu_fast16(fmaf(x1, sc[2 * t + 1], sh[2 * t + 1]));
+                        const __nv_bfloat162 h = __floats2bfloat162_rn(z0, z1);
+                        o[t] = *reinterpret_cast<const uint32_t *>(&h);
+                    }
+                    *cell = make_uint4(o[0], o[1], o[2], o[3]);
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core's reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(a_ready(sa), 0));
+            }
+        }
     } else {
         // ===== epilogue (both CTAs): own 128 pixels; TMEM lane quarter = warp % 4, column block = (warp - 2) / 4 =====
         const int q = warp & 3, part = (warp - 2) >> 2;
-        constexpr int COLS = BN / (EPI_WARPS / 4);
+        constexpr int COLS = BN / (NEPI / 4);
         const uint32_t buf = out_base + (uint32_t)(warp - 2) * OUT_BUF_BYTES;
         uint32_t lt = 0;
         for (int tile = pair_id; tile < n_tiles; tile += n_pairs, ++lt) {
@@ -547,11 +620,18 @@ size_t gp_conv3x3_gn_slabs(int H, int W) {
     return (size_t)(H * W / gp::tc::conv::TILE_PIX) * (conv_pair_mode() ? 8 : 4);
 }
 
-int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream) {
+static int conv3x3_impl(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream,
+                        const float *in_stats, const float *in_gamma, const float *in_beta) {
     using namespace gp::tc;
     using namespace gp::tc::conv;
     if (!x || !w_packed || !y) return GP_ERR_NULL;
     if (N <= 0 || H <= 0 || W <= 0 || Cin <= 0) return GP_ERR_SHAPE;
+    const bool xform = in_stats != nullptr;
+    if (xform) {   // fused GroupNorm(32) + GELU of the producer layer: CTA-pair kernel only, a 16-byte slot = channels of ONE group
+        if (!in_gamma || !in_beta) return GP_ERR_NULL;
+        if (!conv_pair_mode() || (Cin / 32) % 8 || Cin % 32) return GP_ERR_UNSUPPORTED;
+        if ((reinterpret_cast<uintptr_t>(in_gamma) | reinterpret_cast<uintptr_t>(in_beta)) & 15u) return GP_ERR_ALIGN;
+    }
     // 128 output pixels = whole image rows (W divides 128), a 256-pixel tile never straddles two images
     // and a shift by one image row inside the slab stays aligned to the 1024-byte swizzle atom (W >= 8)
     if (Cout != BN || Cin % BK || W > MAX_W || W < 8 || BM % W || (H * W) % TILE_PIX || H % (SUB * (BM / W))) return GP_ERR_UNSUPPORTED;
@@ -565,8 +645,10 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
     if (!sms_of[dev]) {
         cudaError_t e = cudaFuncSetAttribute(conv3x3_gn_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(conv3x3_gn_pair_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pair::P_SMEM_BYTES);
         if (e != cudaSuccess) return (int)e;
         cudaDeviceGetAttribute(&sms_of[dev], cudaDevAttrMultiProcessorCount, dev);
     }
@@ -579,10 +661,14 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
         if (!make_act_map(&mx, x, N, H, W, Cin, BM / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN / 2)) return GP_ERR_UNSUPPORTED;
         const long long pairs = tiles < sms / 2 ? tiles : sms / 2;
         const unsigned grid = (unsigned)(2 * pairs);
-        if (partial)
-            conv3x3_gn_pair_kernel<true><<<grid, CONV_THREADS, pair::P_SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
-        else
-            conv3x3_gn_pair_kernel<false><<<grid, CONV_THREADS, pair::P_SMEM_BYTES, st>>>(mx, mw, my, nullptr, (int)tiles, H * W / TILE_PIX, BM / W, Cin / BK, W * BK * 2);
+        int lgW = 0;
+        while ((1 << lgW) < W) ++lgW;
+#define GP_PAIR_LAUNCH(ST, XF)                                                                                                               \
+    conv3x3_gn_pair_kernel<ST, XF><<<grid, CONV_THREADS, pair::P_SMEM_BYTES, st>>>(mx, mw, my, partial, (int)tiles, H * W / TILE_PIX, BM / W, \
+                                                                                   Cin / BK, W * BK * 2, in_stats, in_gamma, in_beta, H, lgW)
+        if (partial) { if (xform) GP_PAIR_LAUNCH(true, true); else GP_PAIR_LAUNCH(true, false); }
+        else { if (xform) GP_PAIR_LAUNCH(false, true); else GP_PAIR_LAUNCH(false, false); }
+#undef GP_PAIR_LAUNCH
     } else {
         if (!make_act_map(&mx, x, N, H, W, Cin, TILE_PIX / W + 2) || !make_map(&mw, w_packed, BN, 9 * Cin, BN)) return GP_ERR_UNSUPPORTED;
         const unsigned grid = (unsigned)(tiles < sms ? tiles : sms);
@@ -593,6 +679,16 @@ int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *part
     }
     gp::g_launches += 1;
     return (int)cudaGetLastError();
+}
+
+int gp_conv3x3_gn_bf16(const void *x, const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream) {
+    return conv3x3_impl(x, w_packed, y, partial, N, H, W, Cin, Cout, stream, nullptr, nullptr, nullptr);
+}
+
+int gp_conv3x3_gn_bf16_fused_in(const void *x_raw, const float *in_stats, const float *in_gamma, const float *in_beta, const void *w_packed,
+                                void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream) {
+    if (!in_stats) return GP_ERR_NULL;
+    return conv3x3_impl(x_raw, w_packed, y, partial, N, H, W, Cin, Cout, stream, in_stats, in_gamma, in_beta);
 }
 
 }  // extern "C"

@@ -11,6 +11,7 @@
 //                    thread per RoI on the device instead of the reference's per-RoI host loop (:139-157).
 #pragma once
 
+#include "gelu_fast.cuh"
 #include "gp_common.cuh"
 
 namespace gp {
@@ -462,15 +463,6 @@ gn_finalize_kernel(const float *__restrict__ partial, float *__restrict__ stats 
 // tanh.approx.f32 (rel. error 2^-11): total error < 2.5e-4 |x|, an order of magnitude below the bf16 rounding of the
 // stored result.  9 instructions / 1 MUFU instead of ~18 / 2: gn_apply is otherwise bound by the GELU arithmetic, not
 // by HBM.  The fp32 parity mode keeps gelu_erf.
-__device__ __forceinline__ float gelu_fast16(float x) {
-    const float xc = fminf(fmaxf(x, -6.f), 6.f);
-    const float x2 = xc * xc;
-    const float u = xc * fmaf(x2, fmaf(x2, -3.51523083e-4f, 3.70056758e-2f), 7.97507859e-1f);
-    float t;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-    const float hx = 0.5f * x;
-    return fmaf(hx, t, hx);
-}
 
 template <typename T, int ACT> __device__ __forceinline__ float gn_act(float t) {
     if (ACT == ACT_RELU) return fmaxf(t, 0.f);

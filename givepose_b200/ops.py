@@ -212,10 +212,20 @@ def conv3x3_gn_supported(x, cout):
     return cout == 256 and C % 64 == 0 and 8 <= W <= 64 and 128 % W == 0 and (H * W) % 256 == 0 and H % (256 // W) == 0
 
 
-def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True):
+def conv3x3_fused_in_supported(x):
+    """Can ``conv3x3_gn_bf16(..., in_norm=...)`` apply the producer layer's GroupNorm(32) + GELU inside the convolution?  (CTA-pair
+    kernel, input channels a multiple of 256: a 16-byte operand slot then holds channels of one group.)"""
+    return x.dim() == 4 and x.shape[-1] % 256 == 0 and lib.gp_conv3x3_gn_slabs(x.shape[1], x.shape[2]) == 8 * (x.shape[1] * x.shape[2] // 256)
+
+
+def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True, in_norm=None):
     """``Conv2d(Cin, 256, 3, padding=1, bias=False)`` on channel-last bf16 ``x`` (N,H,W,Cin) as a hand-written tcgen05 implicit
     GEMM (``conv3x3_tc.cu``; ``xyz_head.py:195-366`` / ``conv_module.py:57-234``).  Returns ``(y, stats)``: ``y`` (N,H,W,256)
-    bf16 and, if ``stats``, the GroupNorm(32) ``(mean, rstd)`` pairs [N*32*2] of the fp32 accumulators (for ``groupnorm_apply``)."""
+    bf16 and, if ``stats``, the GroupNorm(32) ``(mean, rstd)`` pairs [N*32*2] of the fp32 accumulators (for ``groupnorm_apply``).
+
+    ``in_norm = (in_stats, gamma, beta)``: ``x`` is the RAW output of the previous ConvModule's convolution and that module's
+    GroupNorm + GELU is applied to the operand inside this kernel (bit-identical to ``groupnorm_apply(..., "gelu")`` followed by
+    the plain call, without the pass over the activation); see ``conv3x3_fused_in_supported``."""
     _need_cuda("input", x, torch.bfloat16)
     _need_cuda("weight", w_packed, torch.bfloat16)
     N, H, W, C = x.shape
@@ -228,8 +238,17 @@ def conv3x3_gn_bf16(x, w_packed, groups=32, eps=1e-5, stats=True):
     ws = torch.empty(N * 32 * 2 * (1 + room), dtype=torch.float32, device=x.device) if stats else None
     partial = ws[N * 32 * 2:] if stats else None
     with torch.cuda.device(x.device):
-        check(lib.gp_conv3x3_gn_bf16(_vp(x), _vp(w_packed), _vp(y), _vp(partial) if stats else None, N, H, W, C, Cout, _stream(x)),
-              "conv3x3_gn_bf16")
+        if in_norm is not None:
+            in_stats, gamma, beta = in_norm
+            for n, t in (("in_stats", in_stats), ("gn weight", gamma), ("gn bias", beta)):
+                _need_cuda(n, t, torch.float32)
+            if in_stats.numel() < N * 64 or gamma.numel() != C or beta.numel() != C:
+                raise RuntimeError("conv3x3_gn_bf16: in_norm does not match the input")
+            check(lib.gp_conv3x3_gn_bf16_fused_in(_vp(x), _vp(in_stats), _vp(gamma), _vp(beta), _vp(w_packed), _vp(y),
+                                                  _vp(partial) if stats else None, N, H, W, C, Cout, _stream(x)), "conv3x3_gn_bf16_fused_in")
+        else:
+            check(lib.gp_conv3x3_gn_bf16(_vp(x), _vp(w_packed), _vp(y), _vp(partial) if stats else None, N, H, W, C, Cout, _stream(x)),
+                  "conv3x3_gn_bf16")
         if stats:
             check(lib.gp_groupnorm_finalize(_vp(partial), _vp(ws), N, 32, slabs, H * W * (Cout // 32), float(eps), _stream(x)),
                   "groupnorm_finalize")

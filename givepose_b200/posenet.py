@@ -42,6 +42,11 @@ from .functions import DCNv3Function, dcnv3_forward, dcnv3_forward_packed
 
 # decoder 3x3 convolutions at bf16 inference: 'tc' = the hand-written tcgen05 implicit GEMM (conv3x3_tc.cu), 'cudnn' = library
 DECODER_CONV = os.environ.get("GP_DECODER_CONV", "tc")
+# ConvModule -> ConvModule at one resolution: apply the first module's GroupNorm + GELU inside the second module's convolution
+# (conv3x3_tc.cu XFORM; bit-identical, tests/test_conv3x3_gpu.py).  OFF by default: measured 33 % slower per fused convolution
+# (profiles/r02_it12_fused_input_norm.json) -- every operand element passes through three horizontal-tap slabs with a 2x row halo,
+# so the GELU is evaluated six times per element and the transform needs all of the SM's issue slots.
+DECODER_FUSE_NORM = os.environ.get("GP_DECODER_FUSE_NORM", "0") != "0"
 
 
 @dataclass
@@ -446,10 +451,14 @@ class ConvModule(nn.Module):
                 and self.conv.padding == (1, 1) and self.conv.dilation == (1, 1) and self.conv.groups == 1 and self.conv.bias is None
                 and self.norm.num_groups == 32 and ops.conv3x3_gn_supported(x, self.conv.out_channels))
 
-    def conv_gn_stats(self, x):
-        """conv -> (y, (mean, rstd) pairs of GroupNorm(32) over y); only valid when ``_tc(x)``."""
+    def conv_gn_stats(self, x, in_norm=None):
+        """conv -> (y, (mean, rstd) pairs of GroupNorm(32) over y); only valid when ``_tc(x)``.  ``in_norm``: ``x`` is the raw
+        convolution output of the previous ConvModule, whose GroupNorm + GELU is applied inside this convolution."""
         return ops.conv3x3_gn_bf16(x.contiguous(), _cached(self.conv.weight, torch.bfloat16, ops.pack_conv3x3_weight, "k-major"),
-                                   self.norm.num_groups, self.norm.eps)
+                                   self.norm.num_groups, self.norm.eps, in_norm=in_norm)
+
+    def norm_params(self):
+        return _cached(self.norm.weight, torch.float32), _cached(self.norm.bias, torch.float32)
 
     def forward_nhwc(self, x, upsample2x=False):
         if self._tc(x):
@@ -487,10 +496,32 @@ class TopDownXyzHead(nn.Module):
         """x: (B, 8, 8, in_dim) channel-last -> (B, 64, 64, 3) channel-last."""
         fs = self.features
         x = _gn_act_nhwc(_conv_nhwc(x, fs[0]), fs[1], "gelu")
-        x = fs[3].forward_nhwc(x)
-        x = fs[4].forward_nhwc(x, upsample2x=True)     # features.5: bilinear x2 fused into the GN/GELU apply pass
-        x = fs[6].forward_nhwc(x)
-        x = fs[7].forward_nhwc(x, upsample2x=True)     # features.8
+
+        def pair_of_modules(x, a, b):
+            """ConvModule a -> ConvModule b at one resolution: (raw conv output of b, its GroupNorm statistics), or None when
+            the fused path does not apply.  b's convolution applies a's GroupNorm + GELU to its operand (conv3x3_tc.cu), so
+            a's activation is never written."""
+            if not (DECODER_FUSE_NORM and a._tc(x) and ops.conv3x3_fused_in_supported(x) and a.norm.eps == b.norm.eps):
+                return None
+            ya, sa = a.conv_gn_stats(x)
+            if not b._tc(ya):
+                return None
+            return b.conv_gn_stats(ya, in_norm=(sa,) + a.norm_params())
+
+        def stage(x, a, b, upsample2x):
+            r = pair_of_modules(x, a, b)
+            if r is None:
+                return b.forward_nhwc(a.forward_nhwc(x), upsample2x=upsample2x)
+            return ops.groupnorm_apply(r[0], r[1], *b.norm_params(), b.norm.num_groups, b.norm.eps, "gelu", upsample2x)
+
+        x = stage(x, fs[3], fs[4], True)               # features.5: bilinear x2 after the GN/GELU apply pass
+        x = stage(x, fs[6], fs[7], True)               # features.8
+        last = pair_of_modules(x, fs[9], fs[10]) if (x.shape[-1] == 256 and self.out_layer.out_channels == 3) else None
+        if last is not None:
+            # last ConvModule: conv -> [GN -> GELU -> out_layer 1x1] in one pass; the 256-channel activation is never written
+            return ops.groupnorm_apply_conv1x1(last[0], last[1], *fs[10].norm_params(),
+                                               _cached(self.out_layer.weight, torch.float32, lambda w: w.flatten(1), "rows"),
+                                               _cached(self.out_layer.bias, torch.float32), fs[10].norm.num_groups, fs[10].norm.eps, "gelu")
         x = fs[9].forward_nhwc(x)
         if _fused(x) and x.shape[-1] == 256 and self.out_layer.out_channels == 3:
             # last ConvModule: conv -> [GN -> GELU -> out_layer 1x1] in one pass; the 256-channel activation is never written

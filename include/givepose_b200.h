@@ -212,6 +212,13 @@ int gp_groupnorm_finalize(const float *partial, float *stats, int N, int G, int 
  * Supported: Cout == 256, Cin % 64 == 0, W in {8, 16, 32, 64} with H a multiple of 256/W (whole 256-pixel row blocks).
  * fp32 accumulation over K = 9*Cin in tensor memory; zero padding comes from TMA's out-of-bounds fill. */
 size_t gp_conv3x3_gn_slabs(int H, int W);
+/* The same convolution with the PRODUCER layer's GroupNorm(32) + GELU applied to its operand on the way to the tensor core
+ * (ConvModule -> ConvModule at one resolution, conv_module.py order conv -> norm -> act): x_raw is the raw (un-normalised) output
+ * of the previous convolution, in_stats its (mean, rstd) pairs [N][32][2] (gp_groupnorm_finalize), in_gamma / in_beta [Cin] fp32.
+ * Bit-identical to gp_groupnorm_apply(GELU) followed by gp_conv3x3_gn_bf16, without the apply pass over the activation.
+ * CTA-pair kernel only (gp_conv3x3_set_pair(1), the default); Cin a multiple of 256. */
+int gp_conv3x3_gn_bf16_fused_in(const void *x_raw, const float *in_stats, const float *in_gamma, const float *in_beta,
+                                const void *w_packed, void *y, float *partial, int N, int H, int W, int Cin, int Cout, void *stream);
 /* Kernel variant: 0 = one CTA per 256 x 256 tile (two accumulators = all of TMEM), 1 = CTA pair on one TPC
  * (tcgen05.mma.cta_group::2 M256: half of every weight block per SM, two accumulator sets so the epilogue overlaps the next tile).
  * Returns the previous setting; the initial value comes from GP_CONV_PAIR in the environment.  gp_conv3x3_gn_slabs follows it. */

@@ -129,3 +129,34 @@ def test_conv_module_tc_equals_cudnn_path(res):
             eb = ((b.float() - ref).abs().max() / ref.abs().max()).item()
             assert a.shape == b.shape == ref.shape and ea < 3e-2 and eb < 3e-2, (ea, eb)
             assert ea < 1.5 * eb + 2e-3, (ea, eb)   # not worse than the library path against the fp32 reference
+
+
+@pytest.mark.parametrize("N,H,W", [(3, 16, 16), (2, 32, 32), (2, 64, 64), (150, 16, 16), (37, 32, 32)])
+def test_fused_input_norm_is_bit_identical_to_apply_then_conv(N, H, W, _variant):
+    """ConvModule -> ConvModule: the second convolution applies the first module's GroupNorm + GELU to its operand on the way to
+    the tensor core (transform warps rewrite each TMA slab in place, zero padding left alone).  The operand bits are those
+    gn_apply would have written, the MMAs run in the same order: output and statistics are BIT-IDENTICAL to apply-then-conv."""
+    from givepose_b200 import ops
+    if not _variant:
+        x = torch.zeros(1, 16, 16, 256, dtype=torch.bfloat16).cuda()
+        assert not ops.conv3x3_fused_in_supported(x)      # one-CTA kernel: the fused input path is refused
+        with pytest.raises(RuntimeError):
+            ops.conv3x3_gn_bf16(x, torch.zeros(256, 9 * 256, dtype=torch.bfloat16).cuda(),
+                                in_norm=(torch.zeros(64).cuda(), torch.ones(256).cuda(), torch.zeros(256).cuda()))
+        return
+    x, w0 = _case(N, H, W, 256, 11 + N)
+    g = torch.Generator().manual_seed(N + H)
+    w1 = (torch.randn(256, 256, 3, 3, generator=g) / 48).bfloat16().cuda()
+    gamma = (torch.rand(256, generator=g) + 0.5).cuda()
+    beta = (torch.randn(256, generator=g) * 0.3).cuda()
+    y0, s0 = ops.conv3x3_gn_bf16(x, ops.pack_conv3x3_weight(w0))
+    assert ops.conv3x3_fused_in_supported(y0)
+    z = ops.groupnorm_apply(y0, s0, gamma, beta, 32, 1e-5, "gelu")
+    ref, sref = ops.conv3x3_gn_bf16(z, ops.pack_conv3x3_weight(w1))
+    got, sgot = ops.conv3x3_gn_bf16(y0, ops.pack_conv3x3_weight(w1), in_norm=(s0, gamma, beta))
+    torch.cuda.synchronize()
+    assert torch.equal(got, ref), ((got.float() - ref.float()).abs().max().item(), int((got != ref).sum()))
+    assert torch.equal(sgot, sref)
+    # and against the fp32 composition of the same ops
+    want = F.conv2d(F.gelu(F.group_norm(y0.float().permute(0, 3, 1, 2), 32, gamma, beta, 1e-5)), w1.float(), None, 1, 1).permute(0, 2, 3, 1)
+    assert ((got.float() - want).abs().max() / want.abs().max()).item() < 2e-2
