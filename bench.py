@@ -680,6 +680,7 @@ def main():
         torch.cuda.synchronize()
         return a.elapsed_time(b) / reps
     ms_fwd = timed(lambda: F.dcnv3_forward(inp, off, m, *ARGS, 256, 0), args.steps)
+    fwd_kernel_id = lib.gp_get_option(5)   # GP_OPT_LAST_FWD_KERNEL: which kernel those calls launched
     ms_bwd = timed(lambda: F.dcnv3_backward(inp, off, m, *ARGS, gout, 256, 0), args.steps)
     clocks = sampler.stop() if rank == 0 else None
 
@@ -766,7 +767,8 @@ def main():
     roofline = {"bound": "hbm", "kernel": "dcnv3_bwd_tile (+ grad_input memset)", "achieved": round(ach, 1), "peak": peak,
                 "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes": bwd_b, "ms": round(ms_bwd, 4),
-                "fwd": {"kernel": "dcnv3_fwd_rows (offset / mask rows staged by TMA, 16-byte records)" if lib.gp_get_option(4) == 1 else "dcnv3_fwd_tile", "achieved": round(fwd_b / (ms_fwd * 1e-3) / 1e9, 1),
+                "fwd": {"kernel": {0: "dcnv3_fwd_tile", 1: "dcnv3_fwd_rows (offset / mask rows staged by TMA, 16-byte records)",
+                                   2: "dcnv3_fwd_generic"}.get(fwd_kernel_id, "?"), "achieved": round(fwd_b / (ms_fwd * 1e-3) / 1e9, 1),
                         "frac": round(fwd_b / (ms_fwd * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes": fwd_b, "ms": round(ms_fwd, 4)},
                 "fwd_bwd_frac": round((fwd_b + bwd_b) / ((ms_fwd + ms_bwd) * 1e-3) / 1e9 / peak, 4)}
 

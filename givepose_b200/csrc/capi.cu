@@ -30,6 +30,7 @@ struct Tuning {
     int gin_th = 8, gin_tw = 8;    // output tile of the binned grad_input kernel
     int gin_nt = 192;              // its CTA size
     int fwd_mode = 1;
+    int last_fwd_kernel = -1;      // read-only (GP_OPT_LAST_FWD_KERNEL): 0 dcnv3_fwd_tile, 1 dcnv3_fwd_rows, 2 dcnv3_fwd_generic
     bool init = false;
 };
 #if GP_PART != 2
@@ -395,6 +396,7 @@ static int forward_impl(const void *in, const void *off, const void *msk, void *
             else if (dtype == GP_BF16 && vec == 8) done = launch_fwd_rows<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, dtype, st);
             else if (dtype == GP_F16 && vec == 8) done = launch_fwd_rows<__half, 8, SOFTMAX>(in, off, msk, out, p, L, dtype, st);
         }
+        g_tune.last_fwd_kernel = done ? 1 : 0;
         if (done) return (int)cudaGetLastError();
         if (dtype == GP_F32) launch_fwd_tile<float, 4, SOFTMAX>(in, off, msk, out, p, L, st);
         else if (dtype == GP_BF16 && vec == 8) launch_fwd_tile<__nv_bfloat16, 8, SOFTMAX>(in, off, msk, out, p, L, st);
@@ -402,6 +404,7 @@ static int forward_impl(const void *in, const void *off, const void *msk, void *
         else if (vec == 8) launch_fwd_tile<__half, 8, SOFTMAX>(in, off, msk, out, p, L, st);
         else launch_fwd_tile<__half, 4, SOFTMAX>(in, off, msk, out, p, L, st);
     } else {
+        g_tune.last_fwd_kernel = 2;
         switch (dtype) {
             case GP_F32: launch_fwd_generic<float, SOFTMAX>(in, off, msk, out, p, st); break;
             case GP_BF16: launch_fwd_generic<__nv_bfloat16, SOFTMAX>(in, off, msk, out, p, st); break;
@@ -472,6 +475,7 @@ int gp_get_option(int key) {
         case GP_OPT_GIN_TILE_W: return g_tune.gin_tw;
         case GP_OPT_GIN_THREADS: return g_tune.gin_nt;
         case GP_OPT_FWD_MODE: return g_tune.fwd_mode;
+        case GP_OPT_LAST_FWD_KERNEL: return g_tune.last_fwd_kernel;
     }
     return GP_ERR_SHAPE;
 }

@@ -326,7 +326,8 @@ int gp_set_tuning(int tile_h, int tile_w, int groups_per_cta, int vec16);
  *   GP_OPT_FWD_MODE      0 = dcnv3_fwd_tile (per-thread offset / mask row reads, 24-byte records), 1 = dcnv3_fwd_rows for 3x3
  *                        kernels (default): rows staged by TMA, 16-byte records; other shapes always take mode 0 */
 enum gp_option { GP_OPT_BWD_MODE = 0, GP_OPT_GIN_TILE_H = 1, GP_OPT_GIN_TILE_W = 2, GP_OPT_GIN_THREADS = 3,
-                 GP_OPT_FWD_MODE = 4 };
+                 GP_OPT_FWD_MODE = 4, GP_OPT_LAST_FWD_KERNEL = 5 /* read-only: which kernel the last forward call launched:
+                 0 dcnv3_fwd_tile, 1 dcnv3_fwd_rows, 2 dcnv3_fwd_generic, -1 none yet */ };
 int gp_set_option(int key, int value);
 int gp_get_option(int key);
 

@@ -481,3 +481,26 @@ def test_forward_modes_agree_at_full_size(ops, bwd_options, full_size):
         bwd_options.gp_set_option(OPT_FWD_MODE, mode)
         outs.append(ops.dcnv3_forward(inp, off, m, *args, 256, 0))
     assert _rel(outs[1], outs[0]) < 2e-6
+
+
+def test_forward_kernel_selection_is_observable(ops, bwd_options):
+    """GP_OPT_LAST_FWD_KERNEL reports which kernel a forward call launched: the TMA-row kernel for the benchmark configuration
+    (fp32 and bf16), the per-thread-row kernel when a row pitch is not a multiple of 16 bytes (bf16, G = 2: 72-byte mask rows) or
+    when mode 0 is selected, the generic kernel for odd group widths -- so a silent fall-back cannot hide behind a label."""
+    lib = bwd_options
+    gen = torch.Generator().manual_seed(1)
+
+    def run(N, H, W, G, gc, dtype):
+        inp = torch.randn(N, H, W, G * gc, generator=gen).to("cuda", dtype)
+        off = torch.randn(N, H, W, G * 18, generator=gen).to("cuda", dtype)
+        m = torch.softmax(torch.randn(N, H, W, G, 9, generator=gen), -1).reshape(N, H, W, G * 9).to("cuda", dtype)
+        ops.dcnv3_forward(inp, off, m, 3, 3, 1, 1, 1, 1, 1, 1, G, gc, 1.0, 256, 0)
+        return lib.gp_get_option(5)
+
+    lib.gp_set_option(OPT_FWD_MODE, 1)
+    assert run(2, 64, 64, 8, 32, torch.float32) == 1
+    assert run(2, 64, 64, 8, 32, torch.bfloat16) == 1
+    assert run(2, 16, 16, 2, 32, torch.bfloat16) == 0      # mask rows of 2 * 9 * 2 = 36 bytes: no TMA
+    assert run(1, 9, 9, 2, 30, torch.float32) == 2          # gc = 30: generic kernel
+    lib.gp_set_option(OPT_FWD_MODE, 0)
+    assert run(2, 64, 64, 8, 32, torch.float32) == 0
