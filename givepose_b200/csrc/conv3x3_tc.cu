@@ -295,9 +295,15 @@ conv3x3_gn_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_consta
 // ---------------------------------------------------------------------------------------------------------------------------
 namespace pair {
 constexpr int B_HALF_BYTES = (BN / 2) * BK * 2;          // 16 KB: this CTA's half of a weight block
-constexpr int P_B_STAGES = 6;
+#ifndef GP_P_BSTAGES
+#define GP_P_BSTAGES 6
+#endif
+#ifndef GP_P_SLABS
+#define GP_P_SLABS 3
+#endif
+constexpr int P_B_STAGES = GP_P_BSTAGES;
 constexpr int P_SLAB_BYTES = (BM + 2 * MAX_W) * BK * 2;     // 32 KB: 128/W + 2 rows of W pixels
-constexpr int P_SLABS = 3;
+constexpr int P_SLABS = GP_P_SLABS;
 constexpr int ACCS = 2;                                   // accumulator sets (256 TMEM columns each)
 constexpr size_t P_SMEM_BYTES = 1024 + (size_t)P_SLABS * P_SLAB_BYTES + (size_t)P_B_STAGES * B_HALF_BYTES + OUT_BYTES + 512;
 constexpr uint32_t IDESC2 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
@@ -324,7 +330,10 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                        int rows_per_sub, int kc_blocks, int row_bytes, const float *__restrict__ in_stats /*[N][32][2]*/,
                        const float *__restrict__ in_gamma, const float *__restrict__ in_beta, int H, int lgW) {
     using namespace pair;
-    constexpr int NEPI = XFORM ? 8 : EPI_WARPS;     // epilogue warps (XFORM: warps 2..9, transform warps 10..17)
+#ifndef GP_PAIR_EPI
+#define GP_PAIR_EPI 16
+#endif
+    constexpr int NEPI = XFORM ? 8 : GP_PAIR_EPI;   // epilogue warps (XFORM: warps 2..9, transform warps 10..17)
     constexpr int NXF = 8;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -486,7 +495,7 @@ conv3x3_gn_pair_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_c
                 if (lane == 0) mbar_arrive_cluster(map_to_cta(a_ready(sa), 0));
             }
         }
-    } else {
+    } else if (warp < 2 + NEPI) {
         // ===== epilogue (both CTAs): own 128 pixels; TMEM lane quarter = warp % 4, column block = (warp - 2) / 4 =====
         const int q = warp & 3, part = (warp - 2) >> 2;
         constexpr int COLS = BN / (NEPI / 4);
